@@ -1,0 +1,207 @@
+"""Problem definitions (plain-data dictionaries) for fixtures and benchmarks.
+
+A *problem* is what the reference scripts build with igakit/tIGAr/PENGoLINS
+before the hot path starts: spline patches (knots, homogeneous control points,
+zero-DoFs), material, thickness description, loads and the non-matching
+intersections with their mortar parametric coordinates.
+
+  tbeam()          /root/reference/GOLDFISH/tests/test_tbeam.py:38-117 (BASELINE C2)
+  scordelis_lo()   /root/reference/GOLDFISH/tests/test_slr.py:6-142
+  plate()          /root/reference/demos_csdl_alpha/thickness_opt/plate_const_th_opt_wint.py:12-150
+                   (BASELINE C1; geometry + intersection tables from tests/golden/plate_c1_input.npz)
+  cylinder()       synthetic 8-patch non-matching cylinder (BASELINE C3)
+
+Layout conventions: scalar CP index a = i + j*n_u; patch-local vector dof
+= field*n_cp + a; global dofs = patches concatenated in list order
+(/root/reference/GOLDFISH/nonmatching_opt.py:50-65).
+"""
+import numpy as np
+from . import bsplines as bsp
+
+
+def _side_dofs(n_u, n_v, direction, side, n_layers=1):
+    """tIGAr ``getSideDofs(direction, side, nLayers)`` on the scalar CP grid."""
+    I, J = np.meshgrid(np.arange(n_u), np.arange(n_v), indexing="ij")
+    idx = I if direction == 0 else J
+    n = n_u if direction == 0 else n_v
+    sel = idx < n_layers if side == 0 else idx >= n - n_layers
+    return np.sort((I + J * n_u)[sel])
+
+
+def _patch_from_surface(srf, quad_deg, thickness, bc=(), body_force=(0.0, 0.0, 0.0)):
+    n_u, n_v = srf.control.shape[0], srf.control.shape[1]
+    ncp = n_u * n_v
+    bc_dofs = []
+    for field, direction, side, n_layers in bc:
+        bc_dofs.append(field * ncp + _side_dofs(n_u, n_v, direction, side, n_layers))
+    bc_dofs = np.unique(np.concatenate(bc_dofs)) if bc_dofs else np.zeros(0, dtype=np.int64)
+    return dict(p=tuple(srf.degree), knots=(srf.knots[0].copy(), srf.knots[1].copy()),
+                cp=srf.flat_control(), bc_dofs=bc_dofs.astype(np.int64), quad_deg=int(quad_deg),
+                thickness=dict(thickness), body_force=tuple(body_force))
+
+
+def mortar_coords(ends, n_cells):
+    """PENGoLINS ``move_mortar_mesh`` with two end points: n_cells+1 equally
+    spaced mortar vertices in the parametric space of one side."""
+    ends = np.asarray(ends, dtype=np.float64)
+    if ends.shape[0] != 2:
+        return ends.copy()
+    s = np.linspace(0.0, 1.0, n_cells + 1)[:, None]
+    return ends[0][None, :] * (1.0 - s) + ends[1][None, :] * s
+
+
+def _ruled_quad(pts, n_el0, n_el1, p):
+    """igakit: ruled(line(pts0,pts1), line(pts2,pts3)); elevate to p; refine
+    uniformly (/root/reference/GOLDFISH/tests/test_tbeam.py:5-16)."""
+    srf = bsp.ruled(bsp.line(pts[0], pts[1]), bsp.line(pts[2], pts[3]))
+    srf.elevate(0, p - srf.degree[0]); srf.elevate(1, p - srf.degree[1])
+    srf.refine(0, np.linspace(0, 1, n_el0 + 1)[1:-1])
+    srf.refine(1, np.linspace(0, 1, n_el1 + 1)[1:-1])
+    return srf
+
+
+def tbeam(num_el=10, p=3, E=1.0e7, nu=0.0, h_th=0.1, penalty_coefficient=1.0e3,
+          body_force=(0.0, 0.0, 0.0), tip_load=-10.0, thickness_kind="const",
+          L=20.0, w=2.0, h=2.0, quad_deg_const=3):
+    """Two-patch T-beam (flange + web), one intersection."""
+    pts0 = [[-w / 2., 0., 0.], [w / 2., 0., 0.], [-w / 2., L, 0.], [w / 2., L, 0.]]
+    pts1 = [[0., 0., 0.], [0., 0., -h], [0., L, 0.], [0., L, -h]]
+    n0, n1 = num_el, num_el + 1
+    srf0 = _ruled_quad(pts0, n0 // 2, n0, p)
+    srf1 = _ruled_quad(pts1, n1 // 2, n1, p)
+    bc = [(f, 1, 0, 1) for f in range(3)]  # pin side 0 of direction 1, all fields
+    th = dict(kind=thickness_kind, values=h_th)
+    patches = [_patch_from_surface(s, quad_deg_const * p, th, bc, body_force) for s in (srf0, srf1)]
+    n_m = 2 * n1
+    interfaces = [dict(patches=(0, 1),
+                       xi=(mortar_coords([[0.5, 0.0], [0.5, 1.0]], n_m),
+                           mortar_coords([[0.0, 0.0], [0.0, 1.0]], n_m)))]
+    # PointSource(spline0.V.sub(2), Point(1.,1.), -tip_load): adds -tip_load to R
+    point_loads = [dict(patch=0, field=2, xi=(1.0, 1.0), value=-tip_load)] if tip_load else []
+    return dict(name="tbeam", patches=patches, E=E, nu=nu, interfaces=interfaces,
+                penalty_coefficient=penalty_coefficient, point_loads=point_loads, edge_loads=[])
+
+
+def _roof_patch(num_el, p, R, angle_lim, z_lim):
+    a = (np.radians(angle_lim[0]), np.radians(angle_lim[1]))
+    C = bsp.circle_arc([0, 0, z_lim[0]], R, a)
+    T = bsp.circle_arc([0, 0, z_lim[1]], R, a)
+    S = bsp.ruled(C, T)
+    S.elevate(0, p - S.degree[0]); S.elevate(1, p - S.degree[1])
+    new = np.linspace(0, 1, num_el + 1)[1:-1]
+    S.refine(0, new); S.refine(1, new)
+    return S
+
+
+def scordelis_lo(num_el=6, p=3, penalty_coefficient=1.0e3, quad_deg_const=2):
+    """Nine-patch non-matching Scordelis-Lo roof; QoI_ref = 0.3006 is the
+    vertical displacement at the mid-point of the free edge
+    (/root/reference/GOLDFISH/tests/test_slr.py:40-50)."""
+    L, R = 50.0, 25.0
+    E, nu, h_th = 4.32e8, 0.0, 0.25
+    f = (0.0, -90.0, 0.0)
+    angles = [50, 80, 100, 130]
+    angle_lims = [angles[0:2], angles[1:3], angles[2:4]] * 3
+    z = [0, L / 4, 3 * L / 4, L]
+    z_lims = [z[0:2]] * 3 + [z[1:3]] * 3 + [z[2:4]] * 3
+    ne = num_el
+    nels = [ne, ne - 2, ne - 1, ne + 2, ne + 1, ne + 3, ne - 1, ne, ne - 2]
+    bcs = [[1, 0]] * 3 + [[0, 0]] * 3 + [[0, 1]] * 3
+    patches = []
+    for i in range(9):
+        S = _roof_patch(nels[i], p, R, angle_lims[i], z_lims[i])
+        bc = []
+        for field in (0, 1):
+            for side in (0, 1):
+                if bcs[i][side] == 1:
+                    bc.append((field, 1, side, 1))
+        P = _patch_from_surface(S, quad_deg_const * p, dict(kind="const", values=h_th), bc, f)
+        if i == 0:  # fix_z_node: pin z displacement of control point 0
+            ncp = S.control.shape[0] * S.control.shape[1]
+            P["bc_dofs"] = np.unique(np.concatenate([P["bc_dofs"], [2 * ncp + 0]])).astype(np.int64)
+        patches.append(P)
+    mapping = [[0, 1], [1, 2], [3, 4], [4, 5], [6, 7], [7, 8],
+               [0, 3], [3, 6], [1, 4], [4, 7], [2, 5], [5, 8]]
+    h_locs = [[[0., 1.], [1., 1.]], [[0., 0.], [1., 0.]]]
+    v_locs = [[[1., 0.], [1., 1.]], [[0., 0.], [0., 1.]]]
+    interfaces = []
+    for j, (a, b) in enumerate(mapping):
+        n_m = 3 * (nels[a] + nels[b])
+        locs = v_locs if j < 6 else h_locs
+        interfaces.append(dict(patches=(a, b), xi=(mortar_coords(locs[0], n_m), mortar_coords(locs[1], n_m))))
+    return dict(name="scordelis_lo", patches=patches, E=E, nu=nu, interfaces=interfaces,
+                penalty_coefficient=penalty_coefficient, point_loads=[], edge_loads=[],
+                qoi=dict(patch=3, xi=(0.0, 0.5), field=1, ref=0.3006))
+
+
+def plate(npz_path, E=68e9, nu=0.35, h_th=1.0e-2, penalty_coefficient=1.0e3, load=-100.0,
+          quad_deg_const=4, thickness_kind="linear"):
+    """Six-strip non-matching plate of the CSDL thickness-optimisation demo."""
+    d = np.load(npz_path)
+    patches = []
+    ns = int(d["num_patches"])
+    for s in range(ns):
+        pu, pv = [int(x) for x in d[f"p{s}_deg"]]
+        ku, kv = d[f"p{s}_ku"], d[f"p{s}_kv"]
+        n_u, n_v = len(ku) - pu - 1, len(kv) - pv - 1
+        ncp = n_u * n_v
+        bc = np.zeros(0, dtype=np.int64)
+        if s == 0:  # clampedBC(side=0, direction=0): field 0 one layer, fields 1,2 two layers
+            bc = np.unique(np.concatenate(
+                [f * ncp + _side_dofs(n_u, n_v, 0, 0, 1 if f == 0 else 2) for f in range(3)]))
+        patches.append(dict(p=(pu, pv), knots=(ku, kv), cp=d[f"p{s}_cp"], bc_dofs=bc,
+                            quad_deg=quad_deg_const * pu,
+                            thickness=dict(kind=thickness_kind, values=h_th),
+                            body_force=(0.0, 0.0, 0.0)))
+    interfaces = []
+    for i, (a, b) in enumerate(d["mapping_list"]):
+        interfaces.append(dict(patches=(int(a), int(b)), xi=(d[f"int{i}_xi0"], d[f"int{i}_xi1"])))
+    edge_loads = [dict(patch=ns - 1, direction=0, side=1, traction=(0.0, 0.0, load))]
+    return dict(name="plate", patches=patches, E=E, nu=nu, interfaces=interfaces,
+                penalty_coefficient=penalty_coefficient, point_loads=[], edge_loads=edge_loads)
+
+
+def cylinder(n_el=32, p=3, n_circ=4, n_axial=2, R=1.0, L=4.0, E=68e9, nu=0.35, h_th=1.0e-2,
+             penalty_coefficient=1.0e3, pressure_like_load=(0.0, 0.0, -1.0e3), quad_deg_const=3,
+             thickness_kind="const", arc_deg=360.0, jitter=True):
+    """Synthetic non-matching multi-patch cylinder (BASELINE C3 topology,
+    SURVEY.md section 8d): n_circ arcs x n_axial axial segments, bicubic, patch s
+    has n_el + delta_s elements per side (delta_s = s mod 8) so that meshes do
+    not match along interfaces; one end (z = 0) clamped with two CP layers;
+    dead load per unit area.  arc_deg < 360 gives an open panel."""
+    patches, nels = [], []
+    da = arc_deg / n_circ
+    closed = abs(arc_deg - 360.0) < 1e-12
+    for ia in range(n_axial):
+        for ic in range(n_circ):
+            s = ic + ia * n_circ
+            ne = n_el + ((s % 8) if jitter else 0)
+            nels.append(ne)
+            S = _roof_patch(ne, p, R, [ic * da, (ic + 1) * da], [ia * L / n_axial, (ia + 1) * L / n_axial])
+            bc = []
+            if ia == 0:
+                bc = [(f, 1, 0, 2) for f in range(3)]
+            patches.append(_patch_from_surface(S, quad_deg_const * p, dict(kind=thickness_kind, values=h_th),
+                                               bc, pressure_like_load))
+    v_locs = [[[1., 0.], [1., 1.]], [[0., 0.], [0., 1.]]]
+    h_locs = [[[0., 1.], [1., 1.]], [[0., 0.], [1., 0.]]]
+    interfaces = []
+    for ia in range(n_axial):
+        for ic in range(n_circ):
+            a = ic + ia * n_circ
+            if ic + 1 < n_circ or (closed and n_circ > 1):
+                b = (ic + 1) % n_circ + ia * n_circ
+                n_m = 2 * max(nels[a], nels[b])
+                interfaces.append(dict(patches=(a, b), xi=(mortar_coords(v_locs[0], n_m), mortar_coords(v_locs[1], n_m))))
+            if ia + 1 < n_axial:
+                b = ic + (ia + 1) * n_circ
+                n_m = 2 * max(nels[a], nels[b])
+                interfaces.append(dict(patches=(a, b), xi=(mortar_coords(h_locs[0], n_m), mortar_coords(h_locs[1], n_m))))
+    return dict(name=f"cylinder_{n_circ}x{n_axial}_ne{n_el}", patches=patches, E=E, nu=nu,
+                interfaces=interfaces, penalty_coefficient=penalty_coefficient, point_loads=[],
+                edge_loads=[])
+
+
+def num_dofs(problem):
+    return sum(3 * (len(P["knots"][0]) - P["p"][0] - 1) * (len(P["knots"][1]) - P["p"][1] - 1)
+               for P in problem["patches"])
