@@ -1,0 +1,134 @@
+"""ctypes binding of include/goldfish_b200.h (the C ABI of the CUDA library).
+
+The library is built in-tree by ``__graft_entry__.build()`` into
+``goldfish_b200/libgoldfish_b200.so``.  There is NO CPU fallback: if the
+library or a CUDA device is missing, loading/compute raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgoldfish_b200.so")
+
+GF_OUT_R, GF_OUT_K, GF_OUT_W, GF_OUT_P, GF_OUT_T = 1, 2, 4, 8, 16
+GF_ERRORS = {1: "bad argument", 2: "CUDA error", 3: "not converged", 4: "breakdown", 5: "NaN"}
+
+c_i32, c_i64, c_f64, c_vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p
+
+
+class GfPatchDesc(C.Structure):
+    _fields_ = [("n_u", c_i32), ("n_v", c_i32), ("neu", c_i32), ("nev", c_i32),
+                ("cp_off", c_i32), ("dof_off", c_i32),
+                ("th_off", c_i32), ("th_kind", c_i32), ("nth", c_i32),
+                ("span_u_off", c_i32), ("span_v_off", c_i32),
+                ("cpd_u_off", c_i32), ("cpd_v_off", c_i32),
+                ("rational", c_i32), ("pcol_off", c_i32 * 3), ("el_off", c_i32),
+                ("E", c_f64), ("nu", c_f64), ("f", c_f64 * 3)]
+
+
+class GfCsr(C.Structure):
+    _fields_ = [("nrows", c_i64), ("ncols", c_i64), ("nnz", c_i64),
+                ("indptr", c_vp), ("indices", c_vp), ("vals", c_vp)]
+
+
+class GfModel(C.Structure):
+    _fields_ = [("num_patches", c_i32), ("num_elements", c_i32), ("nq", c_i32), ("num_colors", c_i32),
+                ("N", c_i64), ("n_scalar", c_i64), ("n_th", c_i64),
+                ("patches", c_vp), ("elem_patch", c_vp), ("elem_eu", c_vp), ("elem_ev", c_vp),
+                ("color_elem", c_vp), ("color_ptr_h", c_vp),
+                ("tab_u", c_vp), ("tab_v", c_vp), ("first_cp_u", c_vp), ("first_cp_v", c_vp),
+                ("span_h_u", c_vp), ("span_h_v", c_vp), ("qw", c_vp), ("tw_lin", c_vp),
+                ("cp_lo_u", c_vp), ("cp_hi_u", c_vp), ("el_lo_u", c_vp), ("el_hi_u", c_vp),
+                ("cp_lo_v", c_vp), ("cp_hi_v", c_vp), ("el_lo_v", c_vp), ("el_hi_v", c_vp),
+                ("cp", c_vp), ("u", c_vp), ("theta", c_vp), ("bc", c_vp), ("bc_list", c_vp),
+                ("n_bc", c_i64), ("row_nlow", c_vp),
+                ("K", GfCsr), ("P", GfCsr * 3), ("T", GfCsr)]
+
+
+class GfShellOut(C.Structure):
+    _fields_ = [("R", c_vp), ("WV", c_vp), ("dWdu", c_vp), ("dWdP", c_vp * 3), ("dVdP", c_vp * 3),
+                ("dWdt", c_vp), ("dVdt", c_vp), ("dt_el", c_vp)]
+
+
+class GfPenalty(C.Structure):
+    _fields_ = [("n_eval", c_i64),
+                ("connA", c_vp), ("connB", c_vp), ("connC0", c_vp), ("connC1", c_vp),
+                ("basA", c_vp), ("basB", c_vp), ("basC0", c_vp), ("basC1", c_vp),
+                ("tpar", c_vp), ("alpha", c_vp), ("dofA", c_vp), ("dofB", c_vp),
+                ("g", c_vp), ("Huu", c_vp), ("HuX", c_vp),
+                ("nR", c_i64), ("R_ptr", c_vp), ("R_item", c_vp), ("R_row", c_vp),
+                ("nK", c_i64), ("K_ptr", c_vp), ("K_item", c_vp), ("K_pos", c_vp)]
+
+
+class GfPenaltyP(C.Structure):
+    _fields_ = [("n_dest", c_i64), ("ptr", c_vp), ("item_eval", c_vp), ("item_code", c_vp),
+                ("pos", c_vp), ("vals", c_vp), ("field", c_i32)]
+
+
+class GfCsrT(C.Structure):
+    _fields_ = [("nrows", c_i64), ("nnz", c_i64), ("indptr", c_vp), ("indices", c_vp), ("perm", c_vp)]
+
+
+class GfPcgWork(C.Structure):
+    _fields_ = [("r", c_vp), ("z", c_vp), ("p", c_vp), ("Ap", c_vp), ("dinv", c_vp),
+                ("scal", c_vp), ("partial", c_vp), ("scal_h", c_vp)]
+
+
+# every symbol include/goldfish_b200.h declares, with its argument types
+SIGNATURES = {
+    "gf_shell_assemble": [C.POINTER(GfModel), C.c_int, C.POINTER(GfShellOut), c_vp],
+    "gf_bc_set_diag": [C.POINTER(GfModel), c_f64, c_vp],
+    "gf_penalty_points": [C.POINTER(GfModel), C.POINTER(GfPenalty), C.c_int, c_vp],
+    "gf_penalty_gather_R": [C.POINTER(GfModel), C.POINTER(GfPenalty), c_vp, c_vp],
+    "gf_penalty_gather_K": [C.POINTER(GfModel), C.POINTER(GfPenalty), c_vp],
+    "gf_penalty_gather_P": [C.POINTER(GfPenalty), C.POINTER(GfPenaltyP), c_vp],
+    "gf_mask_vec": [C.POINTER(GfModel), c_vp, c_vp],
+    "gf_spmv": [C.POINTER(GfCsr), c_vp, c_vp, c_f64, c_f64, c_vp],
+    "gf_spmv_t": [C.POINTER(GfCsr), C.POINTER(GfCsrT), c_vp, c_vp, c_f64, c_f64, c_vp],
+    "gf_pcg": [C.POINTER(GfCsr), c_vp, c_vp, C.POINTER(GfPcgWork), c_f64, c_f64, C.c_int, C.c_int,
+               C.POINTER(C.c_int), C.POINTER(c_f64), c_vp],
+    "gf_jacobi_setup": [C.POINTER(GfCsr), c_vp, c_vp],
+    "gf_axpby": [c_i64, c_f64, c_vp, c_f64, c_vp, c_vp],
+    "gf_dot": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "gf_reduce_wv": [c_i64, c_vp, c_vp, c_vp],
+    "gf_last_error": [],
+    "gf_version": [],
+}
+
+_lib = None
+
+
+class GoldfishError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library; raises (never falls back) if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GoldfishError(
+            "goldfish_b200 CUDA library not built: %s is missing "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_char_p if name == "gf_last_error" else C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().gf_last_error()
+        msg = msg.decode() if msg else ""
+        if rc == 3:
+            raise GoldfishNotConverged("%s: %s" % (what, msg))
+        raise GoldfishError("%s failed (%s): %s" % (what, GF_ERRORS.get(rc, rc), msg))
+
+
+class GoldfishNotConverged(GoldfishError):
+    pass

@@ -1,0 +1,19 @@
+// Shared declarations of the goldfish_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/goldfish_b200.h"
+#include "kl_point.cuh"
+
+namespace gf {
+int set_error(int code, const char* msg);
+int set_cuda_error(cudaError_t e, const char* where);
+int check_launch(const char* where);
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+}  // namespace gf

@@ -1,0 +1,312 @@
+// CSR SpMV / SpMV^T, fused Krylov vector kernels and the PCG driver (FP64).
+//
+// Replaces PETSc MatMult / MatMultTranspose (A_x_b / AT_x_b,
+// /root/reference/GOLDFISH/operations/disp_imop.py:68-121) and the MUMPS solves
+// of /root/reference/GOLDFISH/utils/opt_utils.py:156-209 (K is symmetric by
+// construction, nonmatching_opt.py:804-809, so state and adjoint solve share
+// one CG).  All reductions use fixed trees over a fixed grid: results are
+// bit-reproducible from run to run.
+#include "gf_common.cuh"
+
+namespace gf {
+
+constexpr int RED_THREADS = 256;
+constexpr int MAX_PARTIAL = 1024;
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) sh[0] = r;
+  __syncthreads();
+  r = sh[0];
+  return r;
+}
+
+// sum of `n` partials with stride `stride`, identical in every CTA
+__device__ __forceinline__ double sum_partials(const double* p, int n, int stride, double* sh) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += p[(size_t)i * stride];
+  return block_sum(s, sh);
+}
+
+// ---------------------------------------------------------------- SpMV ------
+__global__ void __launch_bounds__(256)
+k_spmv(GfCsr A, const double* __restrict__ x, double* __restrict__ y, double alpha, double beta,
+       const double* __restrict__ dotv, double* __restrict__ partial) {
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  double dacc = 0.0;
+  for (; row < A.nrows; row += nwarps) {
+    const int64_t s = A.indptr[row], e = A.indptr[row + 1];
+    double sum = 0.0;
+    for (int64_t k = s + lane; k < e; k += 32)
+      sum = fma(A.vals[k], __ldg(x + A.indices[k]), sum);
+    sum = warp_sum(sum);
+    if (lane == 0) {
+      double v = alpha * sum;
+      if (beta != 0.0) v = fma(beta, y[row], v);
+      y[row] = v;
+      if (dotv) dacc = fma(dotv[row], v, dacc);
+    }
+  }
+  if (partial) {
+    const double b = block_sum(dacc, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = b;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_spmv_t(GfCsr A, GfCsrT At, const double* __restrict__ x, double* __restrict__ y, double alpha,
+         double beta) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (; row < At.nrows; row += nwarps) {
+    const int64_t s = At.indptr[row], e = At.indptr[row + 1];
+    double sum = 0.0;
+    for (int64_t k = s + lane; k < e; k += 32)
+      sum = fma(A.vals[At.perm[k]], __ldg(x + At.indices[k]), sum);
+    sum = warp_sum(sum);
+    if (lane == 0) {
+      double v = alpha * sum;
+      if (beta != 0.0) v = fma(beta, y[row], v);
+      y[row] = v;
+    }
+  }
+}
+
+static int spmv_grid(int64_t nrows) {
+  int64_t g = (nrows * 32 + 255) / 256;
+  if (g > MAX_PARTIAL) g = MAX_PARTIAL;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------- vector ops ---
+__global__ void k_axpby(int64_t n, double a, const double* x, double b, double* y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = (b == 0.0) ? a * x[i] : fma(a, x[i], b * y[i]);
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+k_dot_partial(int64_t n, const double* x, const double* y, double* partial) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    s = fma(x[i], y[i], s);
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+k_finalize(const double* partial, int n, int stride, double* out) {
+  __shared__ double sh[32];
+  const double s = sum_partials(partial, n, stride, sh);
+  if (threadIdx.x == 0) *out = s;
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+k_reduce_wv(int64_t nel, const double* WV, double* out2) {
+  __shared__ double sh[32];
+  double w = 0.0, v = 0.0;
+  for (int64_t i = threadIdx.x; i < nel; i += blockDim.x) { w += WV[2 * i]; v += WV[2 * i + 1]; }
+  w = block_sum(w, sh);
+  v = block_sum(v, sh);
+  if (threadIdx.x == 0) { out2[0] = w; out2[1] = v; }
+}
+
+static int vec_grid(int64_t n) {
+  int64_t g = (n + RED_THREADS - 1) / RED_THREADS;
+  if (g > MAX_PARTIAL) g = MAX_PARTIAL;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------- PCG ----
+// scal: [0] rz(even) [1] rz(odd) [2] alpha [3] beta [4] rr [5] bb [6] pAp
+__global__ void __launch_bounds__(RED_THREADS)
+k_pcg_init(int64_t n, const double* b, const double* dinv, double* x, double* r, double* z, double* p,
+           double* partial) {
+  __shared__ double sh[32];
+  double rz = 0.0, bb = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double bi = b[i];
+    const double zi = dinv[i] * bi;
+    x[i] = 0.0; r[i] = bi; z[i] = zi; p[i] = zi;
+    rz = fma(bi, zi, rz); bb = fma(bi, bi, bb);
+  }
+  rz = block_sum(rz, sh);
+  bb = block_sum(bb, sh);
+  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = rz; partial[2 * blockIdx.x + 1] = bb; }
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+k_pcg_init_fin(const double* partial, int n, double* scal) {
+  __shared__ double sh[32];
+  const double rz = sum_partials(partial, n, 2, sh);
+  const double bb = sum_partials(partial + 1, n, 2, sh);
+  if (threadIdx.x == 0) { scal[0] = rz; scal[5] = bb; scal[4] = bb; }
+}
+
+// x += alpha p, r -= alpha Ap, z = Dinv r ; partial sums of r.z and r.r
+__global__ void __launch_bounds__(RED_THREADS)
+k_pcg_update(int64_t n, const double* __restrict__ p, const double* __restrict__ Ap,
+             const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
+             double* __restrict__ z, const double* pAp_partial, int npart, double* scal, int parity,
+             double* partial2) {
+  __shared__ double sh[32];
+  const double pAp = sum_partials(pAp_partial, npart, 1, sh);
+  const double alpha = (pAp != 0.0) ? scal[parity] / pAp : 0.0;
+  double rz = 0.0, rr = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double ri = fma(-alpha, Ap[i], r[i]);
+    const double zi = dinv[i] * ri;
+    r[i] = ri; z[i] = zi;
+    rz = fma(ri, zi, rz); rr = fma(ri, ri, rr);
+  }
+  rz = block_sum(rz, sh);
+  rr = block_sum(rr, sh);
+  if (threadIdx.x == 0) {
+    partial2[2 * blockIdx.x] = rz; partial2[2 * blockIdx.x + 1] = rr;
+    if (blockIdx.x == 0) { scal[2] = alpha; scal[6] = pAp; }
+  }
+}
+
+// p = z + beta p
+__global__ void __launch_bounds__(RED_THREADS)
+k_pcg_dir(int64_t n, const double* __restrict__ z, double* __restrict__ p, const double* partial2,
+          int npart, double* scal, int parity) {
+  __shared__ double sh[32];
+  const double rz = sum_partials(partial2, npart, 2, sh);
+  const double rr = sum_partials(partial2 + 1, npart, 2, sh);
+  const double beta = (scal[parity] != 0.0) ? rz / scal[parity] : 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = fma(beta, p[i], z[i]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { scal[1 - parity] = rz; scal[3] = beta; scal[4] = rr; }
+}
+
+__global__ void k_jacobi(GfCsr A, double* dinv) {
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < A.nrows;
+       row += (int64_t)gridDim.x * blockDim.x) {
+    double d = 1.0;
+    for (int64_t k = A.indptr[row]; k < A.indptr[row + 1]; ++k)
+      if (A.indices[k] == row) { d = A.vals[k]; break; }
+    dinv[row] = (d != 0.0) ? 1.0 / d : 1.0;
+  }
+}
+
+__global__ void k_bc_diag(GfModel M, double diag) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M.n_bc; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = M.bc_list[i];
+    for (int64_t k = M.K.indptr[row]; k < M.K.indptr[row + 1]; ++k)
+      M.K.vals[k] = (M.K.indices[k] == row) ? diag : 0.0;
+  }
+}
+
+}  // namespace gf
+
+using namespace gf;
+
+extern "C" int gf_spmv(const GfCsr* A, const double* x, double* y, double alpha, double beta, void* stream) {
+  if (!A || !x || !y) return set_error(GF_ERR_BADARG, "gf_spmv: null argument");
+  if (A->nrows == 0) return GF_OK;
+  k_spmv<<<spmv_grid(A->nrows), 256, 0, (cudaStream_t)stream>>>(*A, x, y, alpha, beta, nullptr, nullptr);
+  return check_launch("k_spmv");
+}
+
+extern "C" int gf_spmv_t(const GfCsr* A, const GfCsrT* At, const double* x, double* y, double alpha,
+                         double beta, void* stream) {
+  if (!A || !At || !x || !y) return set_error(GF_ERR_BADARG, "gf_spmv_t: null argument");
+  if (At->nrows == 0) return GF_OK;
+  k_spmv_t<<<spmv_grid(At->nrows), 256, 0, (cudaStream_t)stream>>>(*A, *At, x, y, alpha, beta);
+  return check_launch("k_spmv_t");
+}
+
+extern "C" int gf_axpby(int64_t n, double a, const double* x, double b, double* y, void* stream) {
+  if (n <= 0) return GF_OK;
+  k_axpby<<<vec_grid(n), RED_THREADS, 0, (cudaStream_t)stream>>>(n, a, x, b, y);
+  return check_launch("k_axpby");
+}
+
+extern "C" int gf_dot(int64_t n, const double* x, const double* y, double* partial, double* out_dev, void* stream) {
+  const int g = vec_grid(n);
+  k_dot_partial<<<g, RED_THREADS, 0, (cudaStream_t)stream>>>(n, x, y, partial);
+  k_finalize<<<1, RED_THREADS, 0, (cudaStream_t)stream>>>(partial, g, 1, out_dev);
+  return check_launch("gf_dot");
+}
+
+extern "C" int gf_reduce_wv(int64_t nel, const double* WV, double* out2_dev, void* stream) {
+  k_reduce_wv<<<1, RED_THREADS, 0, (cudaStream_t)stream>>>(nel, WV, out2_dev);
+  return check_launch("k_reduce_wv");
+}
+
+extern "C" int gf_jacobi_setup(const GfCsr* A, double* dinv, void* stream) {
+  k_jacobi<<<vec_grid(A->nrows), RED_THREADS, 0, (cudaStream_t)stream>>>(*A, dinv);
+  return check_launch("k_jacobi");
+}
+
+extern "C" int gf_bc_set_diag(const GfModel* m, double diag, void* stream) {
+  if (m->n_bc <= 0) return GF_OK;
+  k_bc_diag<<<vec_grid(m->n_bc), RED_THREADS, 0, (cudaStream_t)stream>>>(*m, diag);
+  return check_launch("k_bc_diag");
+}
+
+extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, double rtol,
+                      double atol, int max_it, int check_every, int* iters, double* relres, void* stream) {
+  if (!A || !b || !x || !w) return set_error(GF_ERR_BADARG, "gf_pcg: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = A->nrows;
+  const int gv = vec_grid(n), gs = spmv_grid(n);
+  double* part1 = w->partial;                 // pAp partials [MAX_PARTIAL]
+  double* part2 = w->partial + MAX_PARTIAL;   // (rz, rr) partials [2*MAX_PARTIAL]
+  if (check_every < 1) check_every = 1;
+  k_pcg_init<<<gv, RED_THREADS, 0, st>>>(n, b, w->dinv, x, w->r, w->z, w->p, part2);
+  k_pcg_init_fin<<<1, RED_THREADS, 0, st>>>(part2, gv, w->scal);
+  cudaError_t e = cudaMemcpyAsync(w->scal_h, w->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return set_cuda_error(e, "gf_pcg init");
+  const double bb = w->scal_h[5];
+  int it = 0;
+  double rel = 1.0;
+  if (!(bb > 0.0)) {  // zero right-hand side: x = 0
+    if (iters) *iters = 0;
+    if (relres) *relres = 0.0;
+    return (bb == 0.0) ? GF_OK : set_error(GF_ERR_NAN, "gf_pcg: right-hand side is not finite");
+  }
+  const double bnorm = sqrt(bb);
+  int rc = GF_ERR_NOCONV;
+  while (it < max_it) {
+    const int parity = it & 1;
+    k_spmv<<<gs, 256, 0, st>>>(*A, w->p, w->Ap, 1.0, 0.0, w->p, part1);
+    k_pcg_update<<<gv, RED_THREADS, 0, st>>>(n, w->p, w->Ap, w->dinv, x, w->r, w->z, part1, gs, w->scal,
+                                             parity, part2);
+    k_pcg_dir<<<gv, RED_THREADS, 0, st>>>(n, w->z, w->p, part2, gv, w->scal, parity);
+    ++it;
+    if (it % check_every == 0 || it == max_it) {
+      e = cudaMemcpyAsync(w->scal_h, w->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return set_cuda_error(e, "gf_pcg iteration");
+      const double rr = w->scal_h[4], pAp = w->scal_h[6];
+      if (!(rr == rr) || !(pAp == pAp)) { rc = set_error(GF_ERR_NAN, "gf_pcg: NaN in recurrence"); break; }
+      if (!(pAp > 0.0)) { rc = set_error(GF_ERR_BREAKDOWN, "gf_pcg: p.Ap <= 0 (matrix not SPD)"); break; }
+      rel = sqrt(rr) / bnorm;
+      if (rel < rtol || sqrt(rr) < atol) { rc = GF_OK; break; }
+    }
+  }
+  if (iters) *iters = it;
+  if (relres) *relres = rel;
+  if (rc == GF_ERR_NOCONV) set_error(rc, "gf_pcg: tolerance not reached within max_it");
+  return rc;
+}

@@ -1,0 +1,374 @@
+"""Device-resident model: uploads the symbolic phase to HBM and drives the
+CUDA kernels through the C ABI (include/goldfish_b200.h).
+
+PyTorch is used for device memory and streams only (torch.empty / .data_ptr());
+every number is produced by the hand-written kernels of goldfish_b200/csrc.
+
+HBM layout (all FP64 unless noted):
+  cp     [n_scalar][4]   homogeneous control points, one 32-byte record per CP
+  u      [N]             displacement, per patch field-blocked [ux | uy | uz]
+  theta  [n_th]          thickness dofs
+  K      CSR (int64 indptr, int32 indices, f64 vals), pattern fixed by Symbolic
+  P[f]   CSR shell part of dR/dCP_f  + penP[f] small CSR (penalty part)
+  T      CSR dR/dthickness
+  tab_u/tab_v [spans][nq][3][4]  1-D basis tables at the quadrature points
+"""
+import ctypes as C
+import numpy as np
+import torch
+
+from . import _capi as capi
+from .symbolic import Symbolic
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else C.c_void_p(0)
+
+
+class DeviceCsr:
+    """CSR matrix whose arrays live in HBM."""
+
+    def __init__(self, nrows, ncols, indptr, indices, device):
+        self.nrows, self.ncols = int(nrows), int(ncols)
+        self.indptr_h = np.ascontiguousarray(indptr, dtype=np.int64)
+        self.indices_h = np.ascontiguousarray(indices, dtype=np.int32)
+        self.nnz = int(self.indptr_h[-1])
+        self.indptr = torch.from_numpy(self.indptr_h).to(device)
+        self.indices = torch.from_numpy(self.indices_h).to(device)
+        self.vals = torch.zeros(max(self.nnz, 1), dtype=torch.float64, device=device)
+        self._t = None
+        self.device = device
+
+    def c_struct(self):
+        s = capi.GfCsr()
+        s.nrows, s.ncols, s.nnz = self.nrows, self.ncols, self.nnz
+        s.indptr, s.indices, s.vals = _ptr(self.indptr), _ptr(self.indices), _ptr(self.vals)
+        return s
+
+    def transpose_map(self):
+        """Host-built transpose structure for the deterministic A^T x gather."""
+        if self._t is None:
+            rows = np.repeat(np.arange(self.nrows, dtype=np.int64), np.diff(self.indptr_h))
+            order = np.argsort(self.indices_h, kind="stable")
+            tptr = np.zeros(self.ncols + 1, dtype=np.int64)
+            np.cumsum(np.bincount(self.indices_h, minlength=self.ncols), out=tptr[1:])
+            self._t_arrays = (torch.from_numpy(tptr).to(self.device),
+                              torch.from_numpy(rows[order].astype(np.int32)).to(self.device),
+                              torch.from_numpy(order.astype(np.int64)).to(self.device))
+            t = capi.GfCsrT()
+            t.nrows, t.nnz = self.ncols, self.nnz
+            t.indptr, t.indices, t.perm = [_ptr(a) for a in self._t_arrays]
+            self._t = t
+        return self._t
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.vals[:self.nnz].cpu().numpy(), self.indices_h, self.indptr_h),
+                             shape=(self.nrows, self.ncols))
+
+
+class DeviceModel:
+    def __init__(self, problem, opt_field=(), shopt_surf_inds=(), device=None, symbolic=None):
+        if not torch.cuda.is_available():
+            raise capi.GoldfishError("goldfish_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = capi.load()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.sym = symbolic if symbolic is not None else Symbolic(problem, opt_field, shopt_surf_inds)
+        S = self.sym
+        dv = self.device
+        self._keep = []
+
+        def up(a, dtype=None):
+            a = np.ascontiguousarray(a if dtype is None else np.asarray(a).astype(dtype))
+            t = torch.from_numpy(a).to(dv)
+            self._keep.append(t)
+            return t
+
+        # patch descriptors
+        descs = (capi.GfPatchDesc * len(S.patches))()
+        for d, P in zip(descs, S.patches):
+            d.n_u, d.n_v, d.neu, d.nev = P.n_u, P.n_v, P.neu, P.nev
+            d.cp_off, d.dof_off = P.cp_off, P.dof_off
+            d.th_off, d.th_kind, d.nth = P.th_off, P.th_kind, P.nth
+            d.span_u_off, d.span_v_off, d.cpd_u_off, d.cpd_v_off = P.span_u_off, P.span_v_off, P.cpd_u_off, P.cpd_v_off
+            d.rational = P.rational
+            d.el_off = P.el_off
+            for f in range(3):
+                d.pcol_off[f] = P.pcol_off[f]
+                d.f[f] = float(P.f[f])
+            d.E, d.nu = P.E, P.nu
+        raw = np.frombuffer(bytes(descs), dtype=np.uint8).copy()
+        self.t_patches = up(raw)
+        self.t = {}
+        for k, a, dt in (("elem_patch", S.elem_patch, np.int32), ("elem_eu", S.elem_eu, np.int32),
+                         ("elem_ev", S.elem_ev, np.int32), ("color_elem", S.color_elem, np.int32),
+                         ("tab_u", S.tab_u, np.float64), ("tab_v", S.tab_v, np.float64),
+                         ("first_cp_u", S.first_cp_u, np.int32), ("first_cp_v", S.first_cp_v, np.int32),
+                         ("span_h_u", S.span_h_u, np.float64), ("span_h_v", S.span_h_v, np.float64),
+                         ("qw", S.qw, np.float64), ("tw_lin", S.tw_lin, np.float64),
+                         ("bc", S.bc_mask, np.uint8), ("bc_list", S.bc_list, np.int32),
+                         ("row_nlow", S.row_nlow, np.int32), ("f_const", S.f_const, np.float64)):
+            self.t[k] = up(a, dt)
+        for k, a in S.dirs.items():
+            self.t[k] = up(a, np.int32)
+        self.color_ptr_h = np.ascontiguousarray(S.color_ptr, dtype=np.int32)
+        # state
+        self.cp = up(S.cp0, np.float64)
+        self.u = torch.zeros(S.N, dtype=torch.float64, device=dv)
+        self.theta = up(S.theta0, np.float64)
+        # operators
+        self.K = DeviceCsr(S.N, S.N, S.K_indptr, S.K_indices, dv)
+        self.P = [DeviceCsr(S.N, S.P_ncols[i], S.P_indptr[i], S.P_indices[i], dv) for i in range(len(S.opt_field))]
+        self.T = DeviceCsr(S.N, S.n_th, S.T_indptr, S.T_indices, dv)
+        self.penP = []
+        # outputs
+        self.R = torch.zeros(S.N, dtype=torch.float64, device=dv)
+        self.WV = torch.zeros(max(S.num_elements, 1) * 2, dtype=torch.float64, device=dv)
+        self.wv_sum = torch.zeros(2, dtype=torch.float64, device=dv)
+        self.dWdu = torch.zeros(S.N, dtype=torch.float64, device=dv)
+        self.dWdP = [torch.zeros(max(n, 1), dtype=torch.float64, device=dv) for n in S.P_ncols]
+        self.dVdP = [torch.zeros(max(n, 1), dtype=torch.float64, device=dv) for n in S.P_ncols]
+        self.dWdt = torch.zeros(max(S.n_th, 1), dtype=torch.float64, device=dv)
+        self.dVdt = torch.zeros(max(S.n_th, 1), dtype=torch.float64, device=dv)
+        self.dt_el = torch.zeros(max(S.num_elements, 1) * 2, dtype=torch.float64, device=dv)
+        self._build_penalty(up)
+        self._build_struct()
+        # PCG workspace
+        n = S.N
+        self.w_r, self.w_z, self.w_p, self.w_Ap, self.w_dinv = [torch.zeros(n, dtype=torch.float64, device=dv) for _ in range(5)]
+        self.w_scal = torch.zeros(16, dtype=torch.float64, device=dv)
+        self.w_partial = torch.zeros(4096 * 4, dtype=torch.float64, device=dv)
+        self.w_scal_h = torch.zeros(16, dtype=torch.float64).pin_memory()
+        w = capi.GfPcgWork()
+        w.r, w.z, w.p, w.Ap, w.dinv = [_ptr(t) for t in (self.w_r, self.w_z, self.w_p, self.w_Ap, self.w_dinv)]
+        w.scal, w.partial, w.scal_h = _ptr(self.w_scal), _ptr(self.w_partial), C.c_void_p(self.w_scal_h.data_ptr())
+        self.pcg_work = w
+        self.krylov_rtol = 1e-12
+        self.krylov_max_it = 200000
+        self.krylov_check_every = 50
+        self.last_krylov_its = 0
+        self.last_relres = 0.0
+        self.stats = {"launches": 0}
+        self.state_epoch = 0
+        self._epochs = {}
+
+    def ensure(self, **what):
+        """assemble() only what is stale w.r.t. the current u / design state."""
+        need = {k: True for k, v in what.items() if v and self._epochs.get(k) != self.state_epoch}
+        if need:
+            self.assemble(**need)
+            for k in need:
+                self._epochs[k] = self.state_epoch
+
+    def touch(self):
+        """Mark u / design variables as changed (invalidates cached linearisations)."""
+        self.state_epoch += 1
+
+    # ---------------------------------------------------------------- structs
+    def _build_penalty(self, up):
+        S = self.sym
+        pen = S.pen
+        self.pen_t = {}
+        q = capi.GfPenalty()
+        q.n_eval = pen["n_eval"]
+        if pen["n_eval"] > 0:
+            for k in ("connA", "connB", "connC0", "connC1", "basA", "basB", "basC0", "basC1", "tpar", "alpha",
+                      "dofA", "dofB", "R_ptr", "R_item", "R_row", "K_ptr", "K_item", "K_pos"):
+                self.pen_t[k] = up(pen[k])
+                setattr(q, k, _ptr(self.pen_t[k]))
+            ne = pen["n_eval"]
+            self.pen_g = torch.zeros(ne * 18, dtype=torch.float64, device=self.device)
+            self.pen_Huu = torch.zeros(ne * 324, dtype=torch.float64, device=self.device)
+            self.pen_HuX = torch.zeros(ne * 324, dtype=torch.float64, device=self.device)
+            q.g, q.Huu, q.HuX = _ptr(self.pen_g), _ptr(self.pen_Huu), _ptr(self.pen_HuX)
+            q.nR, q.nK = pen["nR"], pen["nK"]
+            for pp in S.penP:
+                if pp["n_dest"] == 0:
+                    self.penP.append(None)
+                    continue
+                M = DeviceCsr(S.N, S.P_ncols[S.opt_field.index(pp["field"])], pp["indptr"], pp["indices"], self.device)
+                s = capi.GfPenaltyP()
+                s.n_dest = pp["n_dest"]
+                arrs = [up(pp[k]) for k in ("ptr", "item_eval", "item_code", "pos")]
+                s.ptr, s.item_eval, s.item_code, s.pos = [_ptr(a) for a in arrs]
+                s.vals = _ptr(M.vals)
+                s.field = pp["field"]
+                self.penP.append((M, s))
+        else:
+            self.penP = [None for _ in S.opt_field]
+        self.pen_struct = q
+
+    def _build_struct(self):
+        S = self.sym
+        m = capi.GfModel()
+        m.num_patches, m.num_elements, m.nq, m.num_colors = len(S.patches), S.num_elements, S.nq, S.num_colors
+        m.N, m.n_scalar, m.n_th = S.N, S.n_scalar, S.n_th
+        m.patches = _ptr(self.t_patches)
+        for k in ("elem_patch", "elem_eu", "elem_ev", "color_elem", "tab_u", "tab_v", "first_cp_u", "first_cp_v",
+                  "span_h_u", "span_h_v", "qw", "tw_lin", "bc", "bc_list", "row_nlow",
+                  "cp_lo_u", "cp_hi_u", "el_lo_u", "el_hi_u", "cp_lo_v", "cp_hi_v", "el_lo_v", "el_hi_v"):
+            setattr(m, k, _ptr(self.t[k]))
+        m.color_ptr_h = self.color_ptr_h.ctypes.data_as(C.c_void_p)
+        m.cp, m.u, m.theta = _ptr(self.cp), _ptr(self.u), _ptr(self.theta)
+        m.n_bc = len(S.bc_list)
+        m.K = self.K.c_struct()
+        for f in range(3):
+            if f in S.opt_field:
+                m.P[f] = self.P[S.opt_field.index(f)].c_struct()
+        m.T = self.T.c_struct()
+        self.model = m
+        o = capi.GfShellOut()
+        o.R, o.WV, o.dWdu = _ptr(self.R), _ptr(self.WV), _ptr(self.dWdu)
+        for f in range(3):
+            if f in S.opt_field:
+                i = S.opt_field.index(f)
+                o.dWdP[f] = self.dWdP[i].data_ptr()
+                o.dVdP[f] = self.dVdP[i].data_ptr()
+        o.dWdt, o.dVdt = _ptr(self.dWdt), _ptr(self.dVdt)
+        o.dt_el = _ptr(self.dt_el)
+        self.out = o
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ state
+    def set_u(self, u):
+        u = torch.as_tensor(u, dtype=torch.float64)
+        assert u.numel() == self.sym.N
+        self.u.copy_(u.reshape(-1), non_blocking=True)
+        self.touch()
+
+    def set_theta(self, th):
+        th = torch.as_tensor(th, dtype=torch.float64)
+        assert th.numel() == self.sym.n_th
+        self.theta.copy_(th.reshape(-1), non_blocking=True)
+        self.touch()
+
+    def set_cp(self, field, arr, surf_inds=None):
+        S = self.sym
+        if surf_inds is None:
+            surf_inds = range(len(S.patches))
+        arr = torch.as_tensor(arr, dtype=torch.float64).reshape(-1)
+        cpv = self.cp.view(-1, 4)
+        o = 0
+        for s in surf_inds:
+            P = S.patches[s]
+            cpv[P.cp_off:P.cp_off + P.ncp, field].copy_(arr[o:o + P.ncp], non_blocking=True)
+            o += P.ncp
+        assert o == arr.numel()
+        self.touch()
+
+    def get_cp(self, field, surf_inds=None):
+        S = self.sym
+        if surf_inds is None:
+            surf_inds = range(len(S.patches))
+        cpv = self.cp.view(-1, 4)
+        return torch.cat([cpv[S.patches[s].cp_off:S.patches[s].cp_off + S.patches[s].ncp, field] for s in surf_inds])
+
+    # --------------------------------------------------------------- assembly
+    def assemble(self, residual=False, tangent=False, functionals=False, shape=False, thickness=False):
+        """One pass over shells + coupling.  Results stay in HBM:
+        R (BC rows zeroed), K (BCs applied), P[f]/penP[f] (BC rows zeroed), T."""
+        lib, st, S = self.lib, self._stream(), self.sym
+        what = 0
+        if residual:
+            what |= capi.GF_OUT_R; self.R.copy_(self.t["f_const"])
+        if tangent:
+            what |= capi.GF_OUT_K; self.K.vals.zero_()
+        if functionals:
+            what |= capi.GF_OUT_W
+        if shape and S.opt_field:
+            what |= capi.GF_OUT_P
+            for M in self.P:
+                M.vals.zero_()
+            for a in self.dWdP + self.dVdP:
+                a.zero_()
+        if thickness:
+            what |= capi.GF_OUT_T
+            self.T.vals.zero_(); self.dWdt.zero_(); self.dVdt.zero_(); self.dWdu.zero_()
+        if what:
+            capi.check(lib.gf_shell_assemble(C.byref(self.model), what, C.byref(self.out), st), "gf_shell_assemble")
+        if S.pen["n_eval"] > 0 and (residual or tangent or (shape and S.opt_field)):
+            with_X = 1 if (shape and S.opt_field) else 0
+            capi.check(lib.gf_penalty_points(C.byref(self.model), C.byref(self.pen_struct), with_X, st), "gf_penalty_points")
+            if residual:
+                capi.check(lib.gf_penalty_gather_R(C.byref(self.model), C.byref(self.pen_struct), _ptr(self.R), st), "gather_R")
+            if tangent:
+                capi.check(lib.gf_penalty_gather_K(C.byref(self.model), C.byref(self.pen_struct), st), "gather_K")
+            if with_X:
+                for pp in self.penP:
+                    if pp is not None:
+                        pp[0].vals.zero_()
+                        capi.check(lib.gf_penalty_gather_P(C.byref(self.pen_struct), C.byref(pp[1]), st), "gather_P")
+        if residual:
+            capi.check(lib.gf_mask_vec(C.byref(self.model), _ptr(self.R), st), "gf_mask_vec")
+        if tangent:
+            capi.check(lib.gf_bc_set_diag(C.byref(self.model), 1.0, st), "gf_bc_set_diag")
+        if functionals:
+            capi.check(lib.gf_reduce_wv(S.num_elements, _ptr(self.WV), _ptr(self.wv_sum), st), "gf_reduce_wv")
+
+    # ------------------------------------------------------------ linear algebra
+    def spmv(self, A, x, y, alpha=1.0, beta=0.0, transpose=False):
+        st = self._stream()
+        cs = A.c_struct()
+        if transpose:
+            capi.check(self.lib.gf_spmv_t(C.byref(cs), C.byref(A.transpose_map()), _ptr(x), _ptr(y), alpha, beta, st), "gf_spmv_t")
+        else:
+            capi.check(self.lib.gf_spmv(C.byref(cs), _ptr(x), _ptr(y), alpha, beta, st), "gf_spmv")
+        return y
+
+    def axpby(self, a, x, b, y):
+        capi.check(self.lib.gf_axpby(x.numel(), a, _ptr(x), b, _ptr(y), self._stream()), "gf_axpby")
+        return y
+
+    def dot(self, x, y):
+        capi.check(self.lib.gf_dot(x.numel(), _ptr(x), _ptr(y), _ptr(self.w_partial), _ptr(self.w_scal[8:]),
+                                   self._stream()), "gf_dot")
+        return float(self.w_scal[8].item())
+
+    def solve(self, b, x=None, rtol=None, max_it=None, refresh_precond=True):
+        """x = K^{-1} b by preconditioned CG (K symmetric => also K^{-T} b)."""
+        if x is None:
+            x = torch.empty_like(b)
+        st = self._stream()
+        cs = self.K.c_struct()
+        if refresh_precond:
+            capi.check(self.lib.gf_jacobi_setup(C.byref(cs), _ptr(self.w_dinv), st), "gf_jacobi_setup")
+        its = C.c_int(0); rel = C.c_double(0.0)
+        rc = self.lib.gf_pcg(C.byref(cs), _ptr(b), _ptr(x), C.byref(self.pcg_work),
+                             self.krylov_rtol if rtol is None else rtol, 0.0,
+                             self.krylov_max_it if max_it is None else max_it, self.krylov_check_every,
+                             C.byref(its), C.byref(rel), st)
+        self.last_krylov_its, self.last_relres = its.value, rel.value
+        capi.check(rc, "gf_pcg")
+        return x
+
+    def newton(self, max_it=30, rtol=1e-3, verbose=False):
+        """PENGoLINS solve_nonlinear_nonmatching_problem(iga_dofs=True): Newton
+        from u = 0, stop when |R|/|R0| < rtol (disp_imop.py:38-44)."""
+        self.u.zero_()
+        self.touch()
+        ref = None
+        hist, kits = [], []
+        du = torch.empty_like(self.u)
+        rhs = torch.empty_like(self.u)
+        for it in range(max_it + 1):
+            self.assemble(residual=True, tangent=True)
+            nrm = self.dot(self.R, self.R) ** 0.5
+            if it == 0:
+                ref = nrm
+            rel = nrm / ref if ref > 0 else 0.0
+            hist.append(rel)
+            if verbose:
+                print("newton", it, nrm, rel, self.last_krylov_its)
+            if (it > 0 and rel < rtol) or ref == 0.0:
+                break
+            if it == max_it:
+                raise capi.GoldfishNotConverged("Nonlinear solver failed to converge in %d iterations" % max_it)
+            self.axpby(-1.0, self.R, 0.0, rhs)
+            self.solve(rhs, du)
+            kits.append(self.last_krylov_its)
+            self.axpby(1.0, du, 1.0, self.u)
+            self.touch()
+        self.newton_history, self.newton_krylov_its = hist, kits
+        return self.u

@@ -1,0 +1,202 @@
+/* goldfish_b200 -- C ABI of the B200-native analysis + adjoint hot path.
+ *
+ * Drop-in boundary for the arithmetic that the reference reaches through
+ * dolfin/FFC/PETSc/MUMPS from GOLDFISH's NonMatchingOpt.
+ * Plain pointers and sizes only; every pointer inside GfModel is a DEVICE
+ * pointer unless its name ends in _h.  The host language on top is Python
+ * (the reference is Python): goldfish_b200/_capi.py binds these with ctypes.
+ *
+ * Each entry point cites the reference interface it replaces
+ * (paths relative to /root/reference/GOLDFISH/).
+ *
+ * Return value: 0 = ok, GF_ERR_* otherwise (gf_last_error() gives the text).
+ */
+#ifndef GOLDFISH_B200_H
+#define GOLDFISH_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GF_OK 0
+#define GF_ERR_BADARG 1
+#define GF_ERR_CUDA 2
+#define GF_ERR_NOCONV 3   /* Krylov / Newton did not reach the tolerance */
+#define GF_ERR_BREAKDOWN 4
+#define GF_ERR_NAN 5
+
+/* thickness discretisation of a patch */
+#define GF_TH_CONST 0  /* one dof per patch (Function(V_control)/Constant + HthMapComp) */
+#define GF_TH_LINEAR 1 /* CG1 on the two-triangle mesh of knot-span vertices (V_linear) */
+#define GF_TH_IGA 2    /* spline dofs, t = sum_a N_a theta_a (var_thickness=True) */
+
+typedef struct GfPatchDesc {
+  int32_t n_u, n_v;             /* control points per direction                   */
+  int32_t neu, nev;             /* non-empty knot spans (Bezier elements) per dir */
+  int32_t cp_off;               /* first scalar CP in the global scalar numbering */
+  int32_t dof_off;              /* first displacement dof (field-blocked per patch) */
+  int32_t th_off, th_kind, nth; /* thickness dofs                                 */
+  int32_t span_u_off, span_v_off; /* offsets into per-span tables                 */
+  int32_t cpd_u_off, cpd_v_off; /* offsets into per-direction CP tables           */
+  int32_t rational;             /* any weight != 1                                */
+  int32_t pcol_off[3];          /* column offset of the patch in dR/dCP_f, or -1  */
+  int32_t el_off;               /* first element of the patch (global element ids)   */
+  double E, nu;
+  double f[3];                  /* dead load per unit reference area              */
+} GfPatchDesc;
+
+typedef struct GfCsr {          /* CSR with 64-bit row pointers, 32-bit columns   */
+  int64_t nrows, ncols, nnz;
+  const int64_t* indptr;
+  const int32_t* indices;
+  double* vals;
+} GfCsr;
+
+typedef struct GfModel {
+  /* ---- sizes ---- */
+  int32_t num_patches, num_elements, nq, num_colors;
+  int64_t N;                    /* displacement dofs                               */
+  int64_t n_scalar;             /* scalar control points                           */
+  int64_t n_th;                 /* thickness dofs                                  */
+  /* ---- patches / elements ---- */
+  const GfPatchDesc* patches;   /* [num_patches]                                   */
+  const int32_t* elem_patch;    /* [num_elements]                                  */
+  const int32_t* elem_eu;       /* [num_elements] span index in u (0..neu-1)       */
+  const int32_t* elem_ev;
+  const int32_t* color_elem;    /* element ids grouped by colour                   */
+  const int32_t* color_ptr_h;   /* HOST [num_colors+1]                             */
+  /* ---- 1-D basis tables at the element quadrature points ---- */
+  const double* tab_u;          /* [spans_u][nq][3][4] value, d1, d2 of the 4 fns  */
+  const double* tab_v;
+  const int32_t* first_cp_u;    /* [spans_u] first CP index of the span            */
+  const int32_t* first_cp_v;
+  const double* span_h_u;       /* [spans_u] span length                           */
+  const double* span_h_v;
+  const double* qw;             /* [nq] reference weights (sum 1)                  */
+  const double* tw_lin;         /* [nq][4] barycentric weights of (v00,v10,v01,v11) */
+  /* per-direction CP tables: stencil and element ranges of a CP index */
+  const int32_t* cp_lo_u; const int32_t* cp_hi_u; const int32_t* el_lo_u; const int32_t* el_hi_u;
+  const int32_t* cp_lo_v; const int32_t* cp_hi_v; const int32_t* el_lo_v; const int32_t* el_hi_v;
+  /* ---- state ---- */
+  const double* cp;             /* [n_scalar][4] homogeneous control points        */
+  const double* u;              /* [N] displacement (IGA dofs)                     */
+  const double* theta;          /* [n_th] thickness dofs                           */
+  const uint8_t* bc;            /* [N] 1 = zero-dof                                */
+  const int32_t* bc_list;       /* [n_bc] the zero-dofs                            */
+  int64_t n_bc;
+  const int32_t* row_nlow;      /* [n_scalar] coupling columns left of the own block (already x3) */
+  /* ---- operators ---- */
+  GfCsr K;                      /* dR/du, merged shell + penalty pattern           */
+  GfCsr P[3];                   /* shell part of dR/dCP_f (structured)             */
+  GfCsr T;                      /* dR/dthickness                                   */
+} GfModel;
+
+/* What one assembly pass produces (bit mask). */
+#define GF_OUT_R 1      /* residual (shell part incl. dead loads)   -> out_R    */
+#define GF_OUT_K 2      /* tangent                                   -> K.vals   */
+#define GF_OUT_W 4      /* W_int and V, per element                  -> out_WV   */
+#define GF_OUT_P 8      /* dR/dCP_f, dW/dCP_f, dV/dCP_f              -> P[f], out_dWdP, out_dVdP */
+#define GF_OUT_T 16     /* dR/dt, dW/dt, dV/dt, dW/du                -> T, out_dWdt, ... */
+
+typedef struct GfShellOut {
+  double* R;        /* [N]   accumulated (+=); caller zeroes                        */
+  double* WV;       /* [num_elements][2] per-element W_int, V (overwritten)         */
+  double* dWdu;     /* [N]   (+=)                                                   */
+  double* dWdP[3];  /* [ncols of P[f]] (+=)                                         */
+  double* dVdP[3];
+  double* dWdt;     /* [n_th] (+=)                                                  */
+  double* dVdt;
+  double* dt_el;    /* [num_elements][2] per-element dW/dt, dV/dt of GF_TH_CONST patches */
+} GfShellOut;
+
+/* Shell quadrature + scatter.  Replaces assemble(residuals[s]) /
+ * assemble(residuals_deriv[s]) / assemble(dR_dcp_symexp) / assemble(dR_dh_th_symexp)
+ * and the M^T . M extraction products:
+ * nonmatching_opt.py:733-739, :779-781, :852, :936, :688 (AT_R_B), and the
+ * functionals of operations/int_energy_exop.py:55-107, operations/volume_exop.py:46-84. */
+int gf_shell_assemble(const GfModel* m, int what, const GfShellOut* out, void* stream);
+
+/* Zero-dof handling of K after all contributions are in: rows/cols were
+ * masked during scatter; this writes diag = 1 (nonmatching_opt.py:693-700). */
+int gf_bc_set_diag(const GfModel* m, double diag, void* stream);
+
+/* ---- penalty coupling (nonmatching_opt.py:745-752, :789-801, :864-867;
+ *      utils/opt_utils.py:212-260) ---- */
+typedef struct GfPenalty {
+  int64_t n_eval;                 /* (cell, end vertex) evaluations                 */
+  const int32_t* connA;           /* [n_eval][16] global scalar CPs, side A @ v     */
+  const int32_t* connB;           /* [n_eval][16] side B @ v                        */
+  const int32_t* connC0;          /* [n_eval][16] side A @ cell vertex c            */
+  const int32_t* connC1;          /* [n_eval][16] side A @ cell vertex c+1          */
+  const double* basA;             /* [n_eval][3][16] phi, phi_u, phi_v  @ v         */
+  const double* basB;
+  const double* basC0;            /* [n_eval][16] phi @ c                           */
+  const double* basC1;
+  const double* tpar;             /* [n_eval][2]                                    */
+  const double* alpha;            /* [n_eval][2] alpha_d, alpha_r                   */
+  const int32_t* dofA;            /* [n_eval][3] dof_off, ncp, cp_off of patch A    */
+  const int32_t* dofB;
+  /* point results */
+  double* g;                      /* [n_eval][18]                                   */
+  double* Huu;                    /* [n_eval][18][18]                               */
+  double* HuX;                    /* [n_eval][18][18]  d grad_u / d Xv              */
+  /* deterministic gather lists (host-built) */
+  int64_t nR; const int64_t* R_ptr; const int32_t* R_item;   /* item = eval*32 + local node */
+  const int32_t* R_row;           /* [nR][3] destination dofs                       */
+  int64_t nK; const int64_t* K_ptr; const int32_t* K_item;   /* item = eval*1024 + la*32 + lb */
+  const int64_t* K_pos;           /* [nK][9] positions in K.vals, -1 = masked (bc)  */
+} GfPenalty;
+
+int gf_penalty_points(const GfModel* m, const GfPenalty* p, int with_X, void* stream);
+int gf_penalty_gather_R(const GfModel* m, const GfPenalty* p, double* R, void* stream);
+int gf_penalty_gather_K(const GfModel* m, const GfPenalty* p, void* stream);
+
+/* Penalty part of dR/dCP_f, kept as its own small CSR (its pattern reaches
+ * one element beyond the shell stencil through the chord-length term).
+ * One thread per destination (row node, column CP): 3 values (row fields).
+ * item code: la (5 bits: side*16 + a) | xblock << 5 (3 bits) | lb << 8 (4 bits);
+ * xblock: 0 X_A(c), 1 X_A(c+1), 2 X_A,1, 3 X_A,2, 4 X_B,1, 5 X_B,2. */
+typedef struct GfPenaltyP {
+  int64_t n_dest; const int64_t* ptr;
+  const int32_t* item_eval; const int32_t* item_code;
+  const int64_t* pos;             /* [n_dest][3] positions in vals, -1 = masked     */
+  double* vals;
+  int32_t field;
+} GfPenaltyP;
+int gf_penalty_gather_P(const GfPenalty* p, const GfPenaltyP* pp, void* stream);
+/* zero the listed entries of a vector (apply_bcs_vec, nonmatching_opt.py:655) */
+int gf_mask_vec(const GfModel* m, double* v, void* stream);
+
+/* ---- linear algebra (PETSc MatMult/MatMultTranspose, KSP; utils/opt_utils.py:106-209,
+ *      operations/disp_imop.py:58-142) ---- */
+int gf_spmv(const GfCsr* A, const double* x, double* y, double alpha, double beta, void* stream);
+/* y = beta*y + alpha*A^T x through a host-built transpose map (deterministic gather) */
+typedef struct GfCsrT { int64_t nrows, nnz; const int64_t* indptr; const int32_t* indices; const int64_t* perm; } GfCsrT;
+int gf_spmv_t(const GfCsr* A, const GfCsrT* At, const double* x, double* y, double alpha, double beta, void* stream);
+
+typedef struct GfPcgWork {
+  double* r; double* z; double* p; double* Ap;  /* [n] each */
+  double* dinv;       /* [n] inverse diagonal (Jacobi) or 3x3 blocks, see precond */
+  double* scal;       /* [16] device scalars                                        */
+  double* partial;    /* [4096*4] per-CTA partial sums                              */
+  double* scal_h;     /* pinned host [16]                                           */
+} GfPcgWork;
+/* Preconditioned CG on K x = b (K symmetric: nonmatching_opt.py:804-809).
+ * Replaces solve_nonmatching_mat(..., 'direct') (utils/opt_utils.py:176,204). */
+int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, double rtol,
+           double atol, int max_it, int check_every, int* iters, double* relres, void* stream);
+int gf_jacobi_setup(const GfCsr* A, double* dinv, void* stream);
+
+/* small vector helpers on device */
+int gf_axpby(int64_t n, double a, const double* x, double b, double* y, void* stream);
+int gf_dot(int64_t n, const double* x, const double* y, double* partial, double* out_dev, void* stream);
+int gf_reduce_wv(int64_t num_elements, const double* WV, double* out2_dev, void* stream);
+
+const char* gf_last_error(void);
+int gf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def plate_npz():
+    return os.path.join(GOLDEN, "plate_c1_input.npz")
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    import __graft_entry__ as g
+    g.build()
+    from goldfish_b200 import _capi
+    return _capi.load()

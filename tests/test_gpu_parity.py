@@ -1,0 +1,149 @@
+"""GPU: the CUDA path, called through the C ABI, against the oracle on the same
+seeded inputs (BASELINE C1/C2 + Scordelis-Lo).  Tolerances are north_star's:
+patterns bit-exact, assembled matrices/vectors 1e-11 relative, displacements /
+objective / gradients 1e-8 relative."""
+import os
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle.model import OracleModel
+
+pytestmark = pytest.mark.gpu
+TOL_MAT = 1e-11
+TOL_SOL = 1e-8
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def DM(built_lib):
+    from goldfish_b200.device_model import DeviceModel
+    return DeviceModel
+
+
+def _assembled(DM, pr, kw, u):
+    dm = DM(pr, **kw)
+    dm.set_u(u)
+    dm.assemble(residual=True, tangent=True, functionals=True, shape=bool(kw), thickness=True)
+    torch.cuda.synchronize()
+    return dm
+
+
+@pytest.mark.parametrize("case", ["tbeam_small", "slr_small"])
+def test_operators_match_live_oracle(DM, case):
+    pr, kw = getattr(cases, case)()
+    om = OracleModel(pr)
+    u = cases.random_state(om.N, om.bc_global)
+    om.set_u(u)
+    dm = _assembled(DM, pr, kw, u)
+    assert rel(dm.R.cpu().numpy(), om.residual()) < TOL_MAT
+    Kd, Ko = dm.K.to_scipy(), om.stiffness()
+    assert np.array_equal(Kd.indptr, Ko.indptr) and np.array_equal(Kd.indices, Ko.indices)
+    assert abs(Kd - Ko).max() < TOL_MAT * abs(Ko).max()
+    Td, To = dm.T.to_scipy(), om.dRdt()
+    assert np.array_equal(Td.indices, To.indices) and abs(Td - To).max() < TOL_MAT * abs(To).max()
+    W, V = dm.wv_sum.cpu().numpy()
+    assert abs(W - om.energy()) < TOL_MAT * abs(W) and abs(V - om.volume()) < TOL_MAT * abs(V)
+    assert rel(dm.dWdu.cpu().numpy(), om.dWdu(apply_bcs=False)) < TOL_MAT
+    assert rel(dm.dWdt.cpu().numpy()[:om.n_th], om.dWdt()) < TOL_MAT
+    assert rel(dm.dVdt.cpu().numpy()[:om.n_th], om.dVdt()) < TOL_MAT
+    for i, f in enumerate(kw["opt_field"]):
+        A = dm.P[i].to_scipy()
+        if dm.penP[i] is not None:
+            A = A + dm.penP[i][0].to_scipy()
+        A = A.tocsr(); A.sort_indices()
+        Ao = om.dRdCP(f, kw["shopt_surf_inds"][i])
+        assert np.array_equal(A.indices, Ao.indices)
+        assert abs(A - Ao).max() < TOL_MAT * abs(Ao).max()
+        assert rel(dm.dWdP[i].cpu().numpy(), om.dWdCP(f, kw["shopt_surf_inds"][i])) < TOL_MAT
+        assert rel(dm.dVdP[i].cpu().numpy(), om.dVdCP(f, kw["shopt_surf_inds"][i])) < TOL_MAT
+
+
+@pytest.mark.parametrize("case,gold", [("tbeam_c2", "tbeam_c2_golden.npz"), ("plate_c1", "plate_c1_golden.npz")])
+def test_baseline_configs_match_goldens(DM, case, gold):
+    """Full-size C1 / C2 against the committed oracle outputs."""
+    g = np.load(os.path.join(cases.GOLDEN, gold))
+    pr, kw = getattr(cases, case)()
+    dm = _assembled(DM, pr, kw, g["u"])
+    assert rel(dm.R.cpu().numpy(), g["R"]) < TOL_MAT
+    Kd = dm.K.to_scipy()
+    assert np.array_equal(Kd.indptr, g["K_indptr"]) and np.array_equal(Kd.indices, g["K_indices"])
+    assert rel(Kd.data, g["K_data"]) < TOL_MAT
+    Td = dm.T.to_scipy()
+    assert np.array_equal(Td.indices, g["T_indices"]) and rel(Td.data, g["T_data"]) < TOL_MAT
+    W, V = dm.wv_sum.cpu().numpy()
+    assert abs(W - g["W"]) < TOL_MAT * abs(W) and abs(V - g["V"]) < TOL_MAT * abs(V)
+    assert rel(dm.dWdt.cpu().numpy()[:len(g["dWdt"])], g["dWdt"]) < TOL_MAT
+    for i, f in enumerate(kw.get("opt_field", [])):
+        A = (dm.P[i].to_scipy() + dm.penP[i][0].to_scipy()).tocsr(); A.sort_indices()
+        assert np.array_equal(A.indices, g["P%d_indices" % f]) and rel(A.data, g["P%d_data" % f]) < TOL_MAT
+        assert rel(dm.dWdP[i].cpu().numpy(), g["dWdP%d" % f]) < TOL_MAT
+    # Newton from u = 0 with the reference's tolerances, same iterates as the LU path
+    u = dm.newton(max_it=30, rtol=1e-3).cpu().numpy()
+    assert len(dm.newton_history) == len(g["newton_hist"])
+    assert np.linalg.norm(u - g["u_newton"]) < TOL_SOL * np.linalg.norm(g["u_newton"])
+    # objective + adjoint total derivative dW/dt at the Newton state
+    dm.assemble(tangent=True, functionals=True, thickness=True)
+    assert abs(float(dm.wv_sum[0]) - g["W_newton"]) < TOL_SOL * abs(g["W_newton"])
+    rhs = dm.dWdu.clone()
+    rhs[torch.from_numpy(dm.sym.bc_list.astype(np.int64)).cuda()] = 0.0
+    lam = dm.solve(rhs)
+    tot = dm.dWdt[:dm.sym.n_th].clone()
+    dm.spmv(dm.T, lam, tot, alpha=-1.0, beta=1.0, transpose=True)
+    assert np.linalg.norm(tot.cpu().numpy() - g["dWdt_total"]) < TOL_SOL * np.linalg.norm(g["dWdt_total"])
+
+
+def test_bit_reproducible(DM):
+    """Colour-ordered scatter + fixed-tree reductions: identical bits run to run."""
+    pr, kw = cases.tbeam_small()
+    om = OracleModel(pr)
+    u = cases.random_state(om.N, om.bc_global)
+    a = _assembled(DM, pr, kw, u)
+    K1, R1 = a.K.vals.clone(), a.R.clone()
+    x1 = a.solve(a.R.clone()).clone()
+    for _ in range(3):
+        a.touch(); a.assemble(residual=True, tangent=True)
+        assert torch.equal(a.K.vals, K1) and torch.equal(a.R, R1)
+        assert torch.equal(a.solve(a.R.clone()), x1)
+
+
+def test_invariants_at_larger_size(DM):
+    """Size-independent properties on a mesh the oracle would not finish quickly:
+    K symmetric, rigid-body motions in the kernel of the BC-free tangent,
+    dW/dt . t = W_m + 3 W_b is replaced by Euler homogeneity of V in t."""
+    from goldfish_b200 import problems
+    pr = problems.cylinder(n_el=24, n_circ=4, n_axial=2)
+    for P in pr["patches"]:
+        P["bc_dofs"] = np.zeros(0, dtype=np.int64)
+    dm = DM(pr)
+    dm.assemble(tangent=True, functionals=True, thickness=True)
+    K = dm.K.to_scipy()
+    assert abs(K - K.T).max() < 1e-12 * abs(K).max()
+    S = dm.sym
+    for t, w in (((1, 0, 0), (0, 0, 0)), ((0, 0, 0), (0, 0, 1)), ((0, 0, 0), (1, 1, 0))):
+        r = np.zeros(S.N)
+        for P in S.patches:
+            X = P.cp[:, :3] / P.cp[:, 3:4]
+            d = np.array(t, float)[None] + np.cross(np.array(w, float)[None], X)
+            r[P.dof_off:P.dof_off + 3 * P.ncp] = (d * P.cp[:, 3:4]).T.ravel()
+        y = torch.empty(S.N, dtype=torch.float64, device="cuda")
+        dm.spmv(dm.K, torch.from_numpy(r).cuda(), y)
+        assert float(y.abs().max()) < 1e-9 * abs(K).max() * np.abs(r).max()
+    V = float(dm.wv_sum[1]); dV = dm.dVdt[:S.n_th].cpu().numpy()
+    assert abs(dV @ S.theta0 - V) < 1e-12 * V
+    assert abs(V - 2 * np.pi * 1.0 * 4.0 * 1e-2) < 1e-9     # exact NURBS cylinder area x thickness
+
+
+def test_krylov_error_paths(DM):
+    from goldfish_b200 import _capi
+    pr, kw = cases.tbeam_small()
+    dm = DM(pr)
+    dm.assemble(residual=True, tangent=True)
+    with pytest.raises(_capi.GoldfishNotConverged):
+        dm.solve(dm.R.clone(), max_it=3)
+    z = dm.solve(torch.zeros_like(dm.R))
+    assert float(z.abs().max()) == 0.0

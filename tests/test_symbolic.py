@@ -1,0 +1,56 @@
+"""CPU: sparsity patterns and DoF maps of the symbolic phase are bit-exact
+with the oracle (north_star: 'sparsity patterns and DOF maps bit-exact')."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from oracle.model import OracleModel
+from goldfish_b200.symbolic import Symbolic
+import cases
+
+
+@pytest.mark.parametrize("case", ["tbeam_small", "slr_small", "plate_c1"])
+def test_patterns_match_oracle(case):
+    pr, kw = getattr(cases, case)()
+    S = Symbolic(pr, **kw)
+    m = OracleModel(pr)
+    assert S.N == m.N and S.n_th == m.n_th
+    K = m.stiffness()
+    assert np.array_equal(K.indptr, S.K_indptr) and np.array_equal(K.indices, S.K_indices)
+    T = m.dRdt()
+    assert np.array_equal(T.indptr, S.T_indptr) and np.array_equal(T.indices, S.T_indices)
+    assert np.array_equal(np.sort(m.bc_global), S.bc_list)
+    assert np.abs(S.f_const - m.f_const).max() <= 1e-13 * max(1.0, np.abs(m.f_const).max())
+    for fi, f in enumerate(S.opt_field):
+        A = m.dRdCP(f, S.shopt_surf_inds[fi])
+        sh = sp.csr_matrix((np.ones(S.P_indptr[fi][-1]), S.P_indices[fi], S.P_indptr[fi]), shape=A.shape)
+        pp = S.penP[fi]
+        pen = sp.csr_matrix((np.ones(pp["nnz"]), pp["indices"], pp["indptr"]), shape=A.shape)
+        U = (sh + pen).tocsr(); U.sort_indices()
+        assert np.array_equal(U.indptr, A.indptr) and np.array_equal(U.indices, A.indices)
+    al = np.concatenate([np.stack([I.alpha_d[I.ev_v], I.alpha_r[I.ev_v]], 1) for I in m.interfaces])
+    assert np.abs(al - S.pen["alpha"]).max() < 1e-13 * np.abs(al).max()
+
+
+def test_colouring_is_conflict_free():
+    pr, kw = cases.plate_c1()
+    S = Symbolic(pr)
+    for c in range(S.num_colors):
+        els = S.color_elem[S.color_ptr[c]:S.color_ptr[c + 1]]
+        seen = set()
+        for e in els:
+            P = S.patches[S.elem_patch[e]]
+            I0 = P.first_u[S.elem_eu[e]]; J0 = P.first_v[S.elem_ev[e]]
+            cps = {(P.index, I0 + a, J0 + b) for a in range(4) for b in range(4)}
+            assert not (cps & seen)
+            seen |= cps
+
+
+def test_empty_and_ragged_inputs():
+    pr, kw = cases.tbeam_small()
+    pr["interfaces"] = []                                  # no intersections at all
+    S = Symbolic(pr)
+    assert S.pen["n_eval"] == 0 and S.row_nlow.max() == 0
+    pr2, _ = cases.tbeam_small()
+    pr2["patches"][0]["p"] = (2, 3)
+    with pytest.raises(ValueError):
+        Symbolic(pr2)
