@@ -1,0 +1,342 @@
+"""bench.py -- analysis+adjoint iterations/s on the synthetic non-matching
+multi-patch cylinder (BASELINE.json configs[2], SURVEY.md section 8d "C3").
+
+One *step* = one optimizer iteration of the reference stack:
+  design vars -> Newton solve of R(u)=0 from u=0 (rtol 1e-3, max 30)
+  -> W_int, V -> linearize (dR/du, dR/dCP_f for f=0,1,2, dR/dt)
+  -> dW/du, dW/dCP, dW/dt -> adjoint solve K^T lam = dW/du
+  -> total gradients dW/dp - (dR/dp)^T lam.
+
+  python bench.py --gpus N --steps K --warmup W [--n-el NE] [--impl reference]
+
+`value`  : steps/s with the design variables already resident in HBM.
+`e2e`    : steps/s through the reference-facing facade (NonMatchingOpt +
+           operations) with HOST numpy arrays in and out (H2D of the design
+           variables and D2H of state, objective and gradients every step).
+`roofline`: CSR SpMV (the kernel the Krylov solves spend their time in),
+           algorithmic bytes 12 nnz + 24 N + 8 per launch over its CUDA-event time.
+`cpu_baseline` / `--impl reference`: the restated reference CPU path (oracle/,
+           numpy + SuperLU) on a bounded sample of the same topology.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-el", type=int, default=int(os.environ.get("GF_BENCH_NEL", "64")))
+    ap.add_argument("--cpu-n-el", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(n_el):
+    from goldfish_b200 import problems
+    pr = problems.cylinder(n_el=n_el, n_circ=4, n_axial=2, R=1.0, L=4.0, E=68e9, nu=0.35, h_th=1e-2,
+                           pressure_like_load=(0.0, 0.0, -1.0e3), quad_deg_const=3, thickness_kind="const")
+    kw = dict(opt_field=[0, 1, 2], shopt_surf_inds=[list(range(8))] * 3)
+    return pr, kw
+
+
+def design_state(S):
+    """CP perturbation U(-1e-3,1e-3) h_e (seed 0), thickness t(1+0.1U) (seed 1)."""
+    rng = np.random.default_rng(0)
+    cp = S.cp0.copy()
+    for P in S.patches:
+        he = 1.0 / max(P.neu, P.nev)
+        cp[P.cp_off:P.cp_off + P.ncp, :3] += rng.uniform(-1e-3, 1e-3, (P.ncp, 3)) * he
+    th = S.theta0 * (1 + 0.1 * np.random.default_rng(1).uniform(-1, 1, S.n_th))
+    return cp, th
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.samples, self.stop, self.index = [], False, index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in o.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start(); return self
+
+    def __exit__(self, *a):
+        self.stop = True; self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            if len(s) >= 6:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- our arm
+class Step:
+    """One analysis+adjoint iteration on the device model (inputs resident in HBM)."""
+
+    def __init__(self, dm):
+        import torch
+        self.dm, self.torch = dm, torch
+        S = dm.sym
+        self.bc_idx = torch.from_numpy(S.bc_list.astype(np.int64)).to(dm.device)
+        self.lam = torch.zeros(S.N, dtype=torch.float64, device=dm.device)
+        self.rhs = torch.zeros(S.N, dtype=torch.float64, device=dm.device)
+        self.gP = [torch.zeros(n, dtype=torch.float64, device=dm.device) for n in S.P_ncols]
+        self.gT = torch.zeros(S.n_th, dtype=torch.float64, device=dm.device)
+        self.info = {}
+
+    def __call__(self):
+        import ctypes as C
+        from goldfish_b200 import _capi as capi
+        dm, S = self.dm, self.dm.sym
+        dm.newton(max_it=30, rtol=1e-3)
+        kits = list(dm.newton_krylov_its)
+        dm.assemble(tangent=True, functionals=True, shape=True, thickness=True)
+        self.rhs.copy_(dm.dWdu)
+        capi.check(dm.lib.gf_mask_vec(C.byref(dm.model), C.c_void_p(self.rhs.data_ptr()), dm._stream()), "mask")
+        dm.solve(self.rhs, self.lam)
+        kits.append(dm.last_krylov_its)
+        for i in range(len(S.opt_field)):
+            self.gP[i].copy_(dm.dWdP[i][:S.P_ncols[i]])
+            dm.spmv(dm.P[i], self.lam, self.gP[i], alpha=-1.0, beta=1.0, transpose=True)
+            if dm.penP[i] is not None:
+                dm.spmv(dm.penP[i][0], self.lam, self.gP[i], alpha=-1.0, beta=1.0, transpose=True)
+        self.gT.copy_(dm.dWdt[:S.n_th])
+        dm.spmv(dm.T, self.lam, self.gT, alpha=-1.0, beta=1.0, transpose=True)
+        self.info = {"newton_its": len(dm.newton_history) - 1, "krylov_its": kits}
+
+
+def e2e_step(nm, ops, cp_host, th_host):
+    """Same iteration through the reference-facing facade with host arrays."""
+    disp, wint, vol = ops
+    for f in nm.opt_field:
+        nm.update_CPIGA(cp_host[f], f)
+    nm.update_h_th(th_host)
+    u = disp.solve_nonlinear(max_it=30, rtol=1e-3)
+    nm.update_uIGA(u)
+    W, V = wint.Wint(), vol.volume()
+    disp.linearize()
+    dWdu = wint.dWintduIGA()
+    lam = np.zeros_like(u)
+    disp.solve_linear_rev(dWdu, lam)
+    d_in = [np.zeros(nm.vec_scalar_iga_dof) for _ in nm.opt_field] + [np.zeros(nm.h_th_dof)]
+    disp.apply_linear_rev(d_in, None, lam)
+    grads = [wint.dWintdCPIGA(f) - d_in[i] for i, f in enumerate(nm.opt_field)] + [wint.dWintdh_th() - d_in[-1]]
+    return W, V, grads, u
+
+
+def build_facade(pr, kw):
+    from goldfish_b200.nonmatching_opt import NonMatchingOpt, SplinePatch, Thickness, ShellLoad
+    from goldfish_b200.operations import DispImOpeartion, IntEnergyExOperation, VolumeExOperation
+    splines = [SplinePatch(P["knots"], P["p"], P["cp"], P["quad_deg"], P["bc_dofs"]) for P in pr["patches"]]
+    nm = NonMatchingOpt(splines, pr["E"], [Thickness(P["thickness"]["kind"], P["thickness"]["values"]) for P in pr["patches"]], pr["nu"])
+    nm.set_shopt_surf_inds(kw["opt_field"], kw["shopt_surf_inds"])
+    nm.set_thickness_opt(var_thickness=False)
+    nm.create_mortar_meshes([len(it["xi"][0]) - 1 for it in pr["interfaces"]])
+    nm.mortar_meshes_setup([it["patches"] for it in pr["interfaces"]], [it["xi"] for it in pr["interfaces"]],
+                           pr["penalty_coefficient"], 1)
+    nm.set_residuals([ShellLoad(body_force=P["body_force"]) for P in pr["patches"]])
+    return nm, (DispImOpeartion(nm), IntEnergyExOperation(nm), VolumeExOperation(nm))
+
+
+def time_kernel(torch, fn, reps, flush):
+    """Average CUDA-event time of `fn` (ms) with an L2 flush between launches."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for _ in range(3):
+        fn()
+    for a, b in ev:
+        flush.add_(1.0)
+        a.record(); fn(); b.record()
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+
+def cpu_reference_iteration(pr, kw):
+    """The restated reference CPU path (oracle: numpy AD + SuperLU), bounded
+    sample: Newton solve, W/V, tangent, dR/dt, adjoint solve and the thickness
+    gradient.  The three dR/dCP_f passes are left out of the CPU sample (they
+    alone take minutes in the numpy oracle), which makes the CPU side look
+    FASTER than a full iteration would be -- conservative for the ratio."""
+    from oracle.model import OracleModel
+    om = OracleModel(pr)
+    t0 = time.perf_counter()
+    om.solve_nonlinear(max_it=30, rtol=1e-3)
+    W, V = om.energy(), om.volume()
+    K = om.stiffness()
+    T = om.dRdt()
+    lam = om.solve(K, om.dWdu(apply_bcs=True), transpose=True)
+    g = om.dWdt() - T.T @ lam
+    return time.perf_counter() - t0, om.N
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    pr, kw = workload(args.cpu_n_el)
+    full_pr, _ = workload(args.n_el)
+    from goldfish_b200 import problems
+    N_full = problems.num_dofs(full_pr)
+    times = []
+    warm = min(args.warmup, 1)           # CPU code needs no warm-up beyond import/page-in
+    for i in range(warm + args.steps):
+        dt, Ns = cpu_reference_iteration(pr, kw)
+        if i >= warm:
+            times.append(dt)
+    t = float(np.mean(times))
+    val = (1.0 / t) * (Ns / N_full)
+    sample = "cylinder_4x2 at n_el=%d (N=%d): one iteration without the dR/dCP passes, numpy AD + SuperLU; value scaled linearly in DOFs to N=%d" % (args.cpu_n_el, Ns, N_full)
+    line = {"impl": "reference", "metric": "analysis+adjoint iters/s", "value": val, "unit": "iters/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cylinder_4x2_ne%d" % args.n_el, "dofs": N_full},
+            "cpu_baseline": {"value": val, "unit": "iters/s", "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    from goldfish_b200 import _capi as capi
+    from goldfish_b200.device_model import DeviceModel
+    lib = capi.load()
+    pr, kw = workload(args.n_el)
+    dm = DeviceModel(pr, **kw)
+    S = dm.sym
+    cp, th = design_state(S)
+    dm.cp.copy_(torch.from_numpy(cp)); dm.set_theta(th)
+    step = Step(dm)
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float64, device="cuda")  # 512 MB > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = lib.gf_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as cs:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    launches = lib.gf_launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    value = world * args.steps / (ms * 1e-3)      # N>1 currently runs N independent replicas
+
+    # ---- e2e through the facade, host arrays ----
+    nm, ops = build_facade(pr, kw)
+    cp_host = {f: np.concatenate([cp[P.cp_off:P.cp_off + P.ncp, f] for P in S.patches]) for f in kw["opt_field"]}
+    for _ in range(max(1, args.warmup - 1)):
+        e2e_step(nm, ops, cp_host, th)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = e2e_step(nm, ops, cp_host, th)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+    h2d = 8 * (sum(v.size for v in cp_host.values()) + th.size + S.N)            # design vars + update_uIGA
+    d2h = 8 * (S.N * 3 + sum(S.P_ncols) * 2 + S.n_th * 3 + 2)                    # u, dWdu, lam-products, gradients, W, V
+
+    # ---- roofline of the dominant kernel: CSR SpMV ----
+    x = torch.randn(S.N, dtype=torch.float64, device="cuda"); y = torch.empty_like(x)
+    dm.assemble(tangent=True)
+    spmv_ms = time_kernel(torch, lambda: dm.spmv(dm.K, x, y), 20, flush)
+    spmv_bytes = 12 * dm.K.nnz + 24 * S.N + 8
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    # assembly kernels (FP64-pipe bound; reported beside the roofline object)
+    asm_ms = time_kernel(torch, lambda: dm.assemble(tangent=True, residual=True), 5, flush)
+    nq = S.nq
+    asm_flops = S.num_elements * nq * 29376.0
+    kernels = {"spmv_ms": spmv_ms, "spmv_gbs": achieved,
+               "assemble_RK_ms": asm_ms, "assemble_RK_material_tflops": asm_flops / (asm_ms * 1e-3) / 1e12,
+               "assemble_RK_gbs_algorithmic": (8 * dm.K.nnz + 8 * (4 * S.n_scalar + S.N + S.n_th)) / (asm_ms * 1e-3) / 1e9,
+               "newton_its": step.info.get("newton_its"), "krylov_its": step.info.get("krylov_its")}
+
+    if rank == 0:
+        line = {"metric": "analysis+adjoint iters/s", "value": value, "unit": "iters/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "cylinder_4x2_ne%d: 8 non-matching bicubic NURBS patches, 10 intersections, "
+                                       "shape fields 0,1,2 + per-patch thickness" % args.n_el,
+                           "dofs": int(S.N), "elements": int(S.num_elements), "nnz_K": int(dm.K.nnz), "quad_pts_per_element": int(nq),
+                           "cache": "512 MB flush buffer written between timed kernel launches; step working set > L2 at n_el >= 64",
+                           "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world},
+                "e2e": {"value": world * args.steps / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "k_spmv", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"},
+                "kernels": kernels, "clocks": cs.summary()}
+        if not args.no_cpu_baseline:
+            prs, kws = workload(args.cpu_n_el)
+            dt, Ns = cpu_reference_iteration(prs, kws)
+            v = (1.0 / dt) * (Ns / S.N)
+            line["cpu_baseline"] = {"value": v, "unit": "iters/s", "cores": 1, "kind": "port",
+                                    "sample": "one iteration WITHOUT the dR/dCP passes of the oracle (numpy AD + SuperLU) on cylinder_4x2 n_el=%d (N=%d, %.1f s), "
+                                              "scaled linearly in DOFs to N=%d" % (args.cpu_n_el, Ns, dt, S.N)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

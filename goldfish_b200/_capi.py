@@ -93,6 +93,7 @@ SIGNATURES = {
     "gf_reduce_wv": [c_i64, c_vp, c_vp, c_vp],
     "gf_last_error": [],
     "gf_version": [],
+    "gf_launch_count": [],
 }
 
 _lib = None
@@ -116,7 +117,7 @@ def load():
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args
-        fn.restype = C.c_char_p if name == "gf_last_error" else C.c_int
+        fn.restype = C.c_char_p if name == "gf_last_error" else (C.c_longlong if name == "gf_launch_count" else C.c_int)
     _lib = lib
     return lib
 

@@ -9,7 +9,8 @@
 namespace gf {
 int set_error(int code, const char* msg);
 int set_cuda_error(cudaError_t e, const char* where);
-int check_launch(const char* where);
+int check_launch(const char* where);   // also counts one kernel launch
+void count_launch(int n);              // extra launches issued before one check_launch
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -244,6 +244,7 @@ extern "C" int gf_dot(int64_t n, const double* x, const double* y, double* parti
   const int g = vec_grid(n);
   k_dot_partial<<<g, RED_THREADS, 0, (cudaStream_t)stream>>>(n, x, y, partial);
   k_finalize<<<1, RED_THREADS, 0, (cudaStream_t)stream>>>(partial, g, 1, out_dev);
+  count_launch(1);
   return check_launch("gf_dot");
 }
 
@@ -274,6 +275,7 @@ extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWor
   if (check_every < 1) check_every = 1;
   k_pcg_init<<<gv, RED_THREADS, 0, st>>>(n, b, w->dinv, x, w->r, w->z, w->p, part2);
   k_pcg_init_fin<<<1, RED_THREADS, 0, st>>>(part2, gv, w->scal);
+  count_launch(2);
   cudaError_t e = cudaMemcpyAsync(w->scal_h, w->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return set_cuda_error(e, "gf_pcg init");
@@ -293,6 +295,7 @@ extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWor
     k_pcg_update<<<gv, RED_THREADS, 0, st>>>(n, w->p, w->Ap, w->dinv, x, w->r, w->z, part1, gs, w->scal,
                                              parity, part2);
     k_pcg_dir<<<gv, RED_THREADS, 0, st>>>(n, w->z, w->p, part2, gv, w->scal, parity);
+    count_launch(3);
     ++it;
     if (it % check_every == 0 || it == max_it) {
       e = cudaMemcpyAsync(w->scal_h, w->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, st);

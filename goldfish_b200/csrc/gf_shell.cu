@@ -462,7 +462,9 @@ static int launch_mode(const GfModel* m, int what, const GfShellOut* out, cudaSt
     const int b = m->color_ptr_h[c], n = m->color_ptr_h[c + 1] - b;
     if (n <= 0) continue;
     k_shell<MODE><<<(n + 3) / 4, 128, smem, st>>>(*m, *out, what, b, n);
+    count_launch(1);
   }
+  count_launch(-1);
   return check_launch("k_shell");
 }
 

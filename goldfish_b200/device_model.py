@@ -143,7 +143,7 @@ class DeviceModel:
         w.r, w.z, w.p, w.Ap, w.dinv = [_ptr(t) for t in (self.w_r, self.w_z, self.w_p, self.w_Ap, self.w_dinv)]
         w.scal, w.partial, w.scal_h = _ptr(self.w_scal), _ptr(self.w_partial), C.c_void_p(self.w_scal_h.data_ptr())
         self.pcg_work = w
-        self.krylov_rtol = 1e-12
+        self.krylov_rtol = 1e-13
         self.krylov_max_it = 200000
         self.krylov_check_every = 50
         self.last_krylov_its = 0
@@ -342,6 +342,11 @@ class DeviceModel:
         self.last_krylov_its, self.last_relres = its.value, rel.value
         capi.check(rc, "gf_pcg")
         return x
+
+    def dRdCP_matrix(self, i):
+        """dR/dCP of opt-field slot i as one handle (shell + penalty parts)."""
+        from .vecmat import DeviceMat
+        return DeviceMat(self, [self.P[i]] + ([self.penP[i][0]] if self.penP[i] is not None else []))
 
     def newton(self, max_it=30, rtol=1e-3, verbose=False):
         """PENGoLINS solve_nonlinear_nonmatching_problem(iga_dofs=True): Newton

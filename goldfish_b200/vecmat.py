@@ -110,10 +110,14 @@ class DeviceMat:
         self._apply(x.data, y.data, not self.transposed)
 
     def to_scipy(self):
-        A = self.parts[0].to_scipy()
-        for B in self.parts[1:]:
-            A = A + B.to_scipy()
-        A = A.tocsr()
+        """Merged CSR (sorted columns); structural zeros are kept, as PETSc
+        keeps them (scipy's `+` would silently drop entries that sum to 0.0)."""
+        import scipy.sparse as sp
+        mats = [P.to_scipy().tocoo() for P in self.parts]
+        A = sp.coo_matrix((np.concatenate([m.data for m in mats]),
+                           (np.concatenate([m.row for m in mats]), np.concatenate([m.col for m in mats]))),
+                          shape=mats[0].shape).tocsr()
+        A.sum_duplicates()
         A.sort_indices()
         return A.T.tocsr() if self.transposed else A
 

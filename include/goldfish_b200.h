@@ -195,6 +195,8 @@ int gf_reduce_wv(int64_t num_elements, const double* WV, double* out2_dev, void*
 
 const char* gf_last_error(void);
 int gf_version(void);
+/* number of kernels this library has launched so far (bench.py's gpu_launches) */
+long long gf_launch_count(void);
 
 #ifdef __cplusplus
 }

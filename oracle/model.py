@@ -440,6 +440,11 @@ class OracleModel:
     def dRdCP(self, field, surf_inds=None, apply_bcs=True):
         """d R_IGA / d (homogeneous CP coordinate `field`) for the patches in
         surf_inds; columns = concatenated scalar CP dofs of those patches."""
+        return self.dRdCP_fields([field], surf_inds, apply_bcs)[0]
+
+    def dRdCP_fields(self, fields, surf_inds=None, apply_bcs=True):
+        """Same for several fields sharing one AD pass (all fields on the same
+        patch list)."""
         if surf_inds is None:
             surf_inds = list(range(len(self.patches)))
         coloff = {}
@@ -448,7 +453,9 @@ class OracleModel:
             coloff[s] = o
             o += self.patches[s].ncp
         ncol = o
-        rows, cols, vals = [], [], []
+        nf = len(fields)
+        rows, cols = [], []
+        vals = [[] for _ in fields]
         for s in surf_inds:
             P = self.patches[s]
             for sel in self._chunks(P):
@@ -457,19 +464,21 @@ class OracleModel:
                 wq = P.wq[sel]
                 # the X-variables of the jet carry x = X + u with them, so this
                 # mixed block is the total derivative wrt X at fixed u_hom
-                Hux = e.h[:, 15:30, 0:15].reshape(ne, P.nq, 5, 3, 5, 3)
-                Hux = Hux[:, :, :, :, :, field] * wq[:, :, None, None, None]
+                Hux_all = e.h[:, 15:30, 0:15].reshape(ne, P.nq, 5, 3, 5, 3)
                 D5 = P.D[sel][:, :, 1:6]
-                Ae = np.einsum("eqka,eqkil,eqlb->eaib", D5, Hux, D5, optimize=True)
-                # body-force part: -f_i phi_a dJ/dg_X[l,field] D_l phi_b
-                dJ = J.g[:, 0:15].reshape(ne, P.nq, 5, 3)[:, :, :, field] * wq[:, :, None]
-                Ae -= np.einsum("eqa,i,eql,eqlb->eaib", P.D[sel][:, :, 0], P.body_force, dJ, D5,
-                                optimize=True)
                 r = (P.off + np.arange(3)[None, None, :] * P.ncp + P.conn[sel][:, :, None])
                 c = coloff[s] + P.conn[sel]
-                rows.append(np.broadcast_to(r[:, :, :, None], Ae.shape).ravel())
-                cols.append(np.broadcast_to(c[:, None, None, :], Ae.shape).ravel())
-                vals.append(Ae.ravel())
+                shape = (ne, P.nloc, 3, P.nloc)
+                rows.append(np.broadcast_to(r[:, :, :, None], shape).ravel())
+                cols.append(np.broadcast_to(c[:, None, None, :], shape).ravel())
+                for k, field in enumerate(fields):
+                    Hux = Hux_all[:, :, :, :, :, field] * wq[:, :, None, None, None]
+                    Ae = np.einsum("eqka,eqkil,eqlb->eaib", D5, Hux, D5, optimize=True)
+                    # body-force part: -f_i phi_a dJ/dg_X[l,field] D_l phi_b
+                    dJ = J.g[:, 0:15].reshape(ne, P.nq, 5, 3)[:, :, :, field] * wq[:, :, None]
+                    Ae -= np.einsum("eqa,i,eql,eqlb->eaib", P.D[sel][:, :, 0], P.body_force, dJ, D5,
+                                    optimize=True)
+                    vals[k].append(Ae.ravel())
         for I in self.interfaces:
             if I.sA not in coloff and I.sB not in coloff:
                 continue
@@ -477,31 +486,35 @@ class OracleModel:
             Bs = self._penalty_B(I)
             PA, PB = self.patches[I.sA], self.patches[I.sB]
             v, c_ = I.ev_v, I.ev_c
-            # X-variable blocks: (patch, conn, coef[n,16], slice of the 18 X-vars for `field`)
-            Xblocks = []
             HXt = e.h[:, 0:18, 18:36]   # dx = dX + du is formed inside the jets
+            Xblocks = []
             if I.sA in coloff:
-                Xblocks.append((PA, I.connA[c_], I.DA[c_][:, 0, :], 0 + field))
-                Xblocks.append((PA, I.connA[c_ + 1], I.DA[c_ + 1][:, 0, :], 3 + field))
-                Xblocks.append((PA, I.connA[v], I.DA[v][:, 1, :], 6 + field))
-                Xblocks.append((PA, I.connA[v], I.DA[v][:, 2, :], 9 + field))
+                Xblocks.append((PA, I.connA[c_], I.DA[c_][:, 0, :], 0))
+                Xblocks.append((PA, I.connA[c_ + 1], I.DA[c_ + 1][:, 0, :], 3))
+                Xblocks.append((PA, I.connA[v], I.DA[v][:, 1, :], 6))
+                Xblocks.append((PA, I.connA[v], I.DA[v][:, 2, :], 9))
             if I.sB in coloff:
-                Xblocks.append((PB, I.connB[v], I.DB[v][:, 1, :], 12 + field))
-                Xblocks.append((PB, I.connB[v], I.DB[v][:, 2, :], 15 + field))
+                Xblocks.append((PB, I.connB[v], I.DB[v][:, 1, :], 12))
+                Xblocks.append((PB, I.connB[v], I.DB[v][:, 2, :], 15))
             for side, (P0, conn0, coef0) in enumerate(Bs):
                 for (P1, conn1, coef1, xvar) in Xblocks:
                     s1 = self.patches.index(P1)
-                    Hs = HXt[:, 9 * side:9 * side + 9, xvar].reshape(-1, 3, 3)  # (n,kind,comp)
-                    Ae = np.einsum("qka,qki,qb->qaib", coef0, Hs, coef1, optimize=True)
                     r = (P0.off + np.arange(3)[None, None, :] * P0.ncp + conn0[:, :, None])
                     c = coloff[s1] + conn1
-                    rows.append(np.broadcast_to(r[:, :, :, None], Ae.shape).ravel())
-                    cols.append(np.broadcast_to(c[:, None, None, :], Ae.shape).ravel())
-                    vals.append(Ae.ravel())
-        A = self._to_csr(rows, cols, vals, (self.N, ncol))
-        if apply_bcs:
-            A = self._bc_rows(A)
-        return A
+                    shape = (len(v), conn0.shape[1], 3, conn1.shape[1])
+                    rows.append(np.broadcast_to(r[:, :, :, None], shape).ravel())
+                    cols.append(np.broadcast_to(c[:, None, None, :], shape).ravel())
+                    for k, field in enumerate(fields):
+                        Hs = HXt[:, 9 * side:9 * side + 9, xvar + field].reshape(-1, 3, 3)  # (n,kind,comp)
+                        Ae = np.einsum("qka,qki,qb->qaib", coef0, Hs, coef1, optimize=True)
+                        vals[k].append(Ae.ravel())
+        out = []
+        for k in range(nf):
+            A = self._to_csr(rows, cols, vals[k], (self.N, ncol))
+            if apply_bcs:
+                A = self._bc_rows(A)
+            out.append(A)
+        return out
 
     # ----------------------------------------------------------------- dR/dt
     def dRdt(self):
