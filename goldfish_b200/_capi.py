@@ -69,6 +69,15 @@ class GfCsrT(C.Structure):
     _fields_ = [("nrows", c_i64), ("nnz", c_i64), ("indptr", c_vp), ("indices", c_vp), ("perm", c_vp)]
 
 
+class GfSchwarz(C.Structure):
+    _fields_ = [("nblocks", c_i32), ("nb", c_i32), ("max_nbr", c_i32), ("max_mb", c_i32), ("max_n_pad", c_i32),
+                ("ctas_per_block", c_i32), ("n_y", c_i64), ("band_len", c_i64),
+                ("n_pad", c_vp), ("nbr", c_vp), ("off_j", c_vp), ("mbj", c_vp), ("rlen", c_vp), ("off_col", c_vp),
+                ("step_mb_h", c_vp), ("off_y", c_vp), ("off_inv", c_vp),
+                ("glob", c_vp), ("loc", c_vp), ("zptr", c_vp), ("zsrc", c_vp),
+                ("band", c_vp), ("invd", c_vp), ("y", c_vp), ("barrier", c_vp), ("flag", c_vp)]
+
+
 class GfPcgWork(C.Structure):
     _fields_ = [("r", c_vp), ("z", c_vp), ("p", c_vp), ("Ap", c_vp), ("dinv", c_vp),
                 ("scal", c_vp), ("partial", c_vp), ("scal_h", c_vp)]
@@ -85,8 +94,11 @@ SIGNATURES = {
     "gf_mask_vec": [C.POINTER(GfModel), c_vp, c_vp],
     "gf_spmv": [C.POINTER(GfCsr), c_vp, c_vp, c_f64, c_f64, c_vp],
     "gf_spmv_t": [C.POINTER(GfCsr), C.POINTER(GfCsrT), c_vp, c_vp, c_f64, c_f64, c_vp],
-    "gf_pcg": [C.POINTER(GfCsr), c_vp, c_vp, C.POINTER(GfPcgWork), c_f64, c_f64, C.c_int, C.c_int,
+    "gf_pcg": [C.POINTER(GfCsr), c_vp, c_vp, C.POINTER(GfPcgWork), C.POINTER(GfSchwarz), c_f64, c_f64, C.c_int, C.c_int,
                C.POINTER(C.c_int), C.POINTER(c_f64), c_vp],
+    "gf_schwarz_factor": [C.POINTER(GfSchwarz), C.POINTER(GfCsr), c_vp],
+    "gf_schwarz_apply": [C.POINTER(GfSchwarz), c_vp, c_vp, c_i64, c_vp],
+    "gf_dot_slot0": [c_i64, c_vp, c_vp, c_vp, C.c_int, c_vp],
     "gf_jacobi_setup": [C.POINTER(GfCsr), c_vp, c_vp],
     "gf_axpby": [c_i64, c_f64, c_vp, c_f64, c_vp, c_vp],
     "gf_dot": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp],

@@ -264,8 +264,24 @@ extern "C" int gf_bc_set_diag(const GfModel* m, double diag, void* stream) {
   return check_launch("k_bc_diag");
 }
 
-extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, double rtol,
-                      double atol, int max_it, int check_every, int* iters, double* relres, void* stream) {
+// rz partials (slot 0 of partial2) recomputed after a non-diagonal preconditioner
+__global__ void __launch_bounds__(RED_THREADS)
+k_pcg_rz(int64_t n, const double* __restrict__ r, const double* __restrict__ z, double* partial2) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    s = fma(r[i], z[i], s);
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) partial2[2 * blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(RED_THREADS)
+k_pcg_init_p(int64_t n, const double* z, double* p) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = z[i];
+}
+
+extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, const GfSchwarz* pre,
+                      double rtol, double atol, int max_it, int check_every, int* iters, double* relres,
+                      void* stream) {
   if (!A || !b || !x || !w) return set_error(GF_ERR_BADARG, "gf_pcg: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = A->nrows;
@@ -274,6 +290,13 @@ extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWor
   double* part2 = w->partial + MAX_PARTIAL;   // (rz, rr) partials [2*MAX_PARTIAL]
   if (check_every < 1) check_every = 1;
   k_pcg_init<<<gv, RED_THREADS, 0, st>>>(n, b, w->dinv, x, w->r, w->z, w->p, part2);
+  if (pre) {
+    int rc0 = gf_schwarz_apply(pre, w->r, w->z, n, st);
+    if (rc0) return rc0;
+    k_pcg_rz<<<gv, RED_THREADS, 0, st>>>(n, w->r, w->z, part2);
+    k_pcg_init_p<<<gv, RED_THREADS, 0, st>>>(n, w->z, w->p);
+    count_launch(2);
+  }
   k_pcg_init_fin<<<1, RED_THREADS, 0, st>>>(part2, gv, w->scal);
   count_launch(2);
   cudaError_t e = cudaMemcpyAsync(w->scal_h, w->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, st);
@@ -294,6 +317,12 @@ extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWor
     k_spmv<<<gs, 256, 0, st>>>(*A, w->p, w->Ap, 1.0, 0.0, w->p, part1);
     k_pcg_update<<<gv, RED_THREADS, 0, st>>>(n, w->p, w->Ap, w->dinv, x, w->r, w->z, part1, gs, w->scal,
                                              parity, part2);
+    if (pre) {
+      int rc1 = gf_schwarz_apply(pre, w->r, w->z, n, st);
+      if (rc1) return rc1;
+      k_pcg_rz<<<gv, RED_THREADS, 0, st>>>(n, w->r, w->z, part2);
+      count_launch(1);
+    }
     k_pcg_dir<<<gv, RED_THREADS, 0, st>>>(n, w->z, w->p, part2, gv, w->scal, parity);
     count_launch(3);
     ++it;

@@ -68,7 +68,8 @@ class DeviceCsr:
 
 
 class DeviceModel:
-    def __init__(self, problem, opt_field=(), shopt_surf_inds=(), device=None, symbolic=None):
+    def __init__(self, problem, opt_field=(), shopt_surf_inds=(), device=None, symbolic=None,
+                 precond="schwarz", schwarz_layers=2):
         if not torch.cuda.is_available():
             raise capi.GoldfishError("goldfish_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = capi.load()
@@ -143,9 +144,15 @@ class DeviceModel:
         w.r, w.z, w.p, w.Ap, w.dinv = [_ptr(t) for t in (self.w_r, self.w_z, self.w_p, self.w_Ap, self.w_dinv)]
         w.scal, w.partial, w.scal_h = _ptr(self.w_scal), _ptr(self.w_partial), C.c_void_p(self.w_scal_h.data_ptr())
         self.pcg_work = w
+        if precond not in ("schwarz", "jacobi"):
+            raise ValueError("Undefined preconditioner: {}".format(precond))
+        self.precond = precond
+        self.schwarz_layers = schwarz_layers
+        self._sw = None
+        self._sw_factored = False
         self.krylov_rtol = 1e-13
         self.krylov_max_it = 200000
-        self.krylov_check_every = 50
+        self.krylov_check_every = 50 if precond == "jacobi" else 5
         self.last_krylov_its = 0
         self.last_relres = 0.0
         self.stats = {"launches": 0}
@@ -326,16 +333,57 @@ class DeviceModel:
                                    self._stream()), "gf_dot")
         return float(self.w_scal[8].item())
 
-    def solve(self, b, x=None, rtol=None, max_it=None, refresh_precond=True):
-        """x = K^{-1} b by preconditioned CG (K symmetric => also K^{-T} b)."""
+    def _schwarz(self):
+        """Build (once) the overlapping-Schwarz block structure and its HBM storage."""
+        if self._sw is None:
+            from .schwarz import SchwarzSetup, NB
+            A = SchwarzSetup(self.sym, layers=self.schwarz_layers).arrays()
+            dv = self.device
+            t = {k: torch.from_numpy(np.ascontiguousarray(A[k])).to(dv)
+                 for k in ("n_pad", "nbr", "off_j", "mbj", "rlen", "off_col", "off_y", "off_inv", "glob", "loc", "zptr", "zsrc")}
+            t["band"] = torch.zeros(A["band_len"], dtype=torch.float64, device=dv)
+            t["invd"] = torch.zeros(A["inv_len"], dtype=torch.float64, device=dv)
+            t["y"] = torch.zeros(A["n_y"], dtype=torch.float64, device=dv)
+            t["barrier"] = torch.zeros(A["nblocks"], dtype=torch.int32, device=dv)
+            t["flag"] = torch.zeros(1, dtype=torch.int32, device=dv)
+            step_mb = np.ascontiguousarray(A["step_mb"], dtype=np.int32)
+            s = capi.GfSchwarz()
+            s.nblocks, s.nb = A["nblocks"], NB
+            s.max_nbr, s.max_mb, s.max_n_pad = A["max_nbr"], A["max_mb"], A["max_n_pad"]
+            sms = torch.cuda.get_device_properties(dv).multi_processor_count
+            if A["nblocks"] > sms:
+                raise capi.GoldfishError("more Schwarz blocks (patches) than SMs: not supported by the cooperative solve")
+            s.ctas_per_block = max(1, min(32, sms // A["nblocks"]))
+            s.n_y, s.band_len = A["n_y"], A["band_len"]
+            for k in ("n_pad", "nbr", "off_j", "mbj", "rlen", "off_col", "off_y", "off_inv", "glob", "loc", "zptr", "zsrc",
+                      "band", "invd", "y", "barrier", "flag"):
+                setattr(s, k, _ptr(t[k]))
+            s.step_mb_h = step_mb.ctypes.data_as(C.c_void_p)
+            self._sw = (s, t, step_mb, A)
+        return self._sw[0]
+
+    def factor_preconditioner(self):
+        """(Re)build the preconditioner from the current K values."""
+        st = self._stream()
+        cs = self.K.c_struct()
+        if self.precond == "schwarz":
+            capi.check(self.lib.gf_schwarz_factor(C.byref(self._schwarz()), C.byref(cs), st), "gf_schwarz_factor")
+        capi.check(self.lib.gf_jacobi_setup(C.byref(cs), _ptr(self.w_dinv), st), "gf_jacobi_setup")
+        self._sw_factored = True
+
+    def solve(self, b, x=None, rtol=None, max_it=None, refactor=None):
+        """x = K^{-1} b by preconditioned CG (K symmetric => also K^{-T} b).
+        The preconditioner is factored on first use and whenever refactor=True;
+        otherwise the last factorisation is reused (lagged preconditioner)."""
         if x is None:
             x = torch.empty_like(b)
         st = self._stream()
         cs = self.K.c_struct()
-        if refresh_precond:
-            capi.check(self.lib.gf_jacobi_setup(C.byref(cs), _ptr(self.w_dinv), st), "gf_jacobi_setup")
+        if refactor or not self._sw_factored:
+            self.factor_preconditioner()
+        pre = C.byref(self._schwarz()) if self.precond == "schwarz" else None
         its = C.c_int(0); rel = C.c_double(0.0)
-        rc = self.lib.gf_pcg(C.byref(cs), _ptr(b), _ptr(x), C.byref(self.pcg_work),
+        rc = self.lib.gf_pcg(C.byref(cs), _ptr(b), _ptr(x), C.byref(self.pcg_work), pre,
                              self.krylov_rtol if rtol is None else rtol, 0.0,
                              self.krylov_max_it if max_it is None else max_it, self.krylov_check_every,
                              C.byref(its), C.byref(rel), st)
@@ -371,7 +419,7 @@ class DeviceModel:
             if it == max_it:
                 raise capi.GoldfishNotConverged("Nonlinear solver failed to converge in %d iterations" % max_it)
             self.axpby(-1.0, self.R, 0.0, rhs)
-            self.solve(rhs, du)
+            self.solve(rhs, du, refactor=(it == 0))
             kits.append(self.last_krylov_its)
             self.axpby(1.0, du, 1.0, self.u)
             self.touch()

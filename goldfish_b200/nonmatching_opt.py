@@ -278,7 +278,7 @@ class NonMatchingOpt:
         dm.assemble(residual=True, tangent=True)
         rhs = torch.empty_like(dm.R)
         dm.axpby(-1.0, dm.R, 0.0, rhs)
-        dm.solve(rhs, dm.u); dm.touch()
+        dm.solve(rhs, dm.u, refactor=True); dm.touch()
         u = DeviceVec(dm.u, self.vec_iga_dof_list, dm)
         return (None, u) if iga_dofs else None
 

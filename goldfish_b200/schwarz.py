@@ -1,0 +1,142 @@
+"""Host set-up of the overlapping additive-Schwarz preconditioner (once per topology).
+
+One block per patch: the patch's control points plus ``layers`` graph layers of
+the neighbouring patches' control points across each intersection (the scalar
+CP graph is the K pattern collapsed over the 3 fields).  Inside a block the
+nodes are ordered so that the block matrix is BANDED: own nodes in natural
+order (slow index = the longer parametric direction), overlap nodes inserted
+at the row of their nearest own node plus their offset along the slow
+direction.  3 dofs per node are interleaved.  csrc/gf_schwarz.cu factors and
+solves the bands; this file only produces index arrays.
+
+Mirrors PENGoLINS' ``solve_nonmatching_mat(..., solver='ksp')`` (CG +
+additive PCFIELDSPLIT with per-patch LU), with overlap.
+"""
+import numpy as np
+import scipy.sparse as sp
+from scipy.spatial import cKDTree
+
+NB = 64
+
+
+class SchwarzSetup:
+    def __init__(self, sym, layers=2):
+        S = sym
+        self.sym, self.layers = sym, layers
+        n_s = S.n_scalar
+        # scalar CP graph: own stencils + coupled pairs
+        rows, cols = [], []
+        for P in S.patches:
+            cand, mask, _ = S._own_stencil(P)
+            a, m = np.nonzero(mask)
+            rows.append(P.cp_off + a); cols.append(P.cp_off + cand[a, m])
+        if len(S.cpl_keys):
+            rows.append(S.cpl_keys // n_s); cols.append(S.cpl_keys % n_s)
+        r = np.concatenate(rows); c = np.concatenate(cols)
+        G = sp.csr_matrix((np.ones(len(r), dtype=np.int8), (r, c)), shape=(n_s, n_s))
+        G.sum_duplicates()
+        self.G = G
+        dof = np.array([P.dof_off for P in S.patches]); ncp = np.array([P.ncp for P in S.patches])
+        cpo = np.array([P.cp_off for P in S.patches])
+        Xall = S.cp0[:, :3] / S.cp0[:, 3:4]
+        self.blocks = []
+        for P in S.patches:
+            own = np.arange(P.cp_off, P.cp_off + P.ncp)
+            cur = own
+            for _ in range(layers):
+                cur = np.union1d(cur, G[cur].indices)
+            extra = np.setdiff1d(cur, own)
+            # natural keys of own nodes; slow direction = the one with more CPs
+            I = (own - P.cp_off) % P.n_u; J = (own - P.cp_off) // P.n_u
+            swap = P.n_u > P.n_v
+            slow_own, fast_own = (I, J) if swap else (J, I)
+            ks, kf = slow_own.astype(np.float64), fast_own.astype(np.float64)
+            if len(extra):
+                Xo = Xall[own].reshape(P.n_v, P.n_u, 3)
+                tree = cKDTree(Xall[own])
+                _, nn = tree.query(Xall[extra])
+                In, Jn = I[nn], J[nn]
+
+                def direction(di, dj):
+                    a_i = np.clip(In + di, 0, P.n_u - 1); a_j = np.clip(Jn + dj, 0, P.n_v - 1)
+                    b_i = np.clip(In - di, 0, P.n_u - 1); b_j = np.clip(Jn - dj, 0, P.n_v - 1)
+                    d = Xo[a_j, a_i] - Xo[b_j, b_i]
+                    steps = (a_i - b_i) + (a_j - b_j)
+                    h = np.linalg.norm(d, axis=1) / np.maximum(steps, 1)
+                    e = d / np.maximum(np.linalg.norm(d, axis=1), 1e-300)[:, None]
+                    return e, np.maximum(h, 1e-300)
+                eu, hu = direction(1, 0); ev, hv = direction(0, 1)
+                off = Xall[extra] - Xall[own][nn]
+                ou = (off * eu).sum(1) / hu; ov = (off * ev).sum(1) / hv
+                s_e, f_e = (In + ou, Jn + ov) if swap else (Jn + ov, In + ou)
+                ks = np.concatenate([ks, s_e]); kf = np.concatenate([kf, f_e])
+            nodes = np.concatenate([own, extra])
+            order = np.lexsort((kf, ks))
+            nodes = nodes[order]
+            # node bandwidth from the induced subgraph
+            pos = np.full(n_s, -1, dtype=np.int64); pos[nodes] = np.arange(len(nodes))
+            sub = G[nodes]
+            pr = np.repeat(np.arange(len(nodes)), np.diff(sub.indptr)); pc = pos[sub.indices]
+            ok = pc >= 0
+            beta = int(np.abs(pr[ok] - pc[ok]).max())
+            n = 3 * len(nodes)
+            bw = 3 * beta + 2
+            n_pad = ((n + NB - 1) // NB) * NB
+            nbr_ = n_pad // NB
+            # block-row envelope: first block column reached by each block row
+            # (dof = 3*node + field; fields couple fully, so use node extremes)
+            first_node = np.full(len(nodes), len(nodes), dtype=np.int64)
+            np.minimum.at(first_node, pr[ok], pc[ok])
+            row_blk = (3 * np.arange(len(nodes)) + 2) // NB          # last dof of the node
+            row_blk0 = (3 * np.arange(len(nodes))) // NB             # first dof of the node
+            fc = np.arange(nbr_, dtype=np.int64)
+            np.minimum.at(fc, row_blk, (3 * first_node) // NB)
+            np.minimum.at(fc, row_blk0, (3 * first_node) // NB)
+            for b_ in range(nbr_ - 2, -1, -1):                       # monotone envelope
+                fc[b_] = min(fc[b_], fc[b_ + 1])
+            rlen = np.arange(nbr_) - fc
+            mbj = np.zeros(nbr_, dtype=np.int64)
+            last = np.searchsorted(fc, np.arange(nbr_), side="right") - 1   # last row whose envelope reaches col j
+            mbj = np.maximum(last - np.arange(nbr_), 0)
+            ps = S.scalar_patch[nodes]
+            glob = np.full(n_pad, -1, dtype=np.int32)
+            for f in range(3):
+                glob[f:n:3] = dof[ps] + f * ncp[ps] + (nodes - cpo[ps])
+            self.blocks.append(dict(nodes=nodes, n=n, n_pad=n_pad, bw=bw, nbr=nbr_, mbj=mbj.astype(np.int32),
+                                    rlen=rlen.astype(np.int32), mb=int(mbj.max()), glob=glob, n_own=P.ncp))
+
+    def arrays(self):
+        """Flat index arrays for GfSchwarz."""
+        S = self.sym
+        nb = len(self.blocks)
+        n_pad = np.array([b["n_pad"] for b in self.blocks], dtype=np.int32)
+        nbr = np.array([b["nbr"] for b in self.blocks], dtype=np.int32)
+        mbj = np.concatenate([b["mbj"] for b in self.blocks]).astype(np.int32)
+        rlen = np.concatenate([b["rlen"] for b in self.blocks]).astype(np.int32)
+        off_j = np.concatenate([[0], np.cumsum(nbr.astype(np.int64))[:-1]]).astype(np.int64)
+        col_sz = (mbj.astype(np.int64) + 1) * NB * NB
+        off_col = np.concatenate([[0], np.cumsum(col_sz)[:-1]]).astype(np.int64)
+        band_len = int(col_sz.sum())
+        step_mb = np.zeros(int(nbr.max()), dtype=np.int32)
+        for b in self.blocks:
+            step_mb[:b["nbr"]] = np.maximum(step_mb[:b["nbr"]], b["mbj"])
+        off_y = np.concatenate([[0], np.cumsum(n_pad.astype(np.int64))[:-1]]).astype(np.int64)
+        inv_sz = nbr.astype(np.int64) * NB * NB
+        off_inv = np.concatenate([[0], np.cumsum(inv_sz)[:-1]]).astype(np.int64)
+        glob = np.concatenate([b["glob"] for b in self.blocks])
+        loc = np.full((nb, S.N), -1, dtype=np.int32)
+        for i, b in enumerate(self.blocks):
+            g = b["glob"]; m = g >= 0
+            loc[i, g[m]] = np.nonzero(m)[0]
+        # prolongation gather: dof d <- every block-local copy, in block order
+        src = np.nonzero(glob >= 0)[0]
+        d = glob[src]
+        o = np.argsort(d, kind="stable")
+        zsrc = src[o].astype(np.int64)
+        zptr = np.zeros(S.N + 1, dtype=np.int64)
+        np.cumsum(np.bincount(d, minlength=S.N), out=zptr[1:])
+        return dict(nblocks=nb, n_pad=n_pad, nbr=nbr, off_j=off_j, mbj=mbj, rlen=rlen, off_col=off_col,
+                    step_mb=step_mb, off_y=off_y, off_inv=off_inv,
+                    glob=glob.astype(np.int32), loc=loc, zptr=zptr, zsrc=zsrc, n_y=int(n_pad.sum()),
+                    band_len=band_len, inv_len=int(inv_sz.sum()),
+                    max_nbr=int(nbr.max()), max_mb=int(mbj.max()), max_n_pad=int(n_pad.max()))

@@ -175,6 +175,37 @@ int gf_spmv(const GfCsr* A, const double* x, double* y, double alpha, double bet
 typedef struct GfCsrT { int64_t nrows, nnz; const int64_t* indptr; const int32_t* indices; const int64_t* perm; } GfCsrT;
 int gf_spmv_t(const GfCsr* A, const GfCsrT* At, const double* x, double* y, double alpha, double beta, void* stream);
 
+/* Overlapping additive Schwarz with banded block-Cholesky sub-solves (the CG +
+ * per-patch-LU fieldsplit option of PENGoLINS, SURVEY.md Appendix A.5, made
+ * overlapping so the penalty springs sit inside a block).  goldfish_b200/schwarz.py
+ * builds the block orderings; all arrays are device pointers except *_h. */
+typedef struct GfSchwarz {
+  int32_t nblocks, nb;            /* nb = 64                                          */
+  int32_t max_nbr, max_mb, max_n_pad, ctas_per_block;
+  int64_t n_y, band_len;          /* total padded local dofs; band storage length     */
+  const int32_t* n_pad;           /* [nblocks] padded local size (multiple of nb)     */
+  const int32_t* nbr;             /* [nblocks] block rows                             */
+  const int64_t* off_j;           /* [nblocks] offsets into the per-block-column arrays */
+  const int32_t* mbj;             /* [sum nbr] panel height (blocks below the diagonal) of each block column */
+  const int32_t* rlen;            /* [sum nbr] blocks left of the diagonal in each block row */
+  const int64_t* off_col;         /* [sum nbr] offset of each block column's panel in band */
+  const int32_t* step_mb_h;       /* HOST [max_nbr] max panel height per step over the blocks */
+  const int64_t* off_y;           /* [nblocks] offsets into y / glob                  */
+  const int64_t* off_inv;         /* [nblocks] offsets into invd                      */
+  const int32_t* glob;            /* [n_y] local -> global dof, -1 = padding          */
+  const int32_t* loc;             /* [nblocks][N] global -> local dof, -1 = absent    */
+  const int64_t* zptr;            /* [N+1] prolongation gather                        */
+  const int64_t* zsrc;            /* [..] indices into y                              */
+  double* band;                   /* factor storage: nb x nb blocks                   */
+  double* invd;                   /* inverses of the diagonal factor blocks           */
+  double* y;                      /* [n_y] block-local vectors                        */
+  uint32_t* barrier;              /* [nblocks] group barrier counters                 */
+  int32_t* flag;                  /* device flag: non-SPD block met                   */
+} GfSchwarz;
+int gf_schwarz_factor(const GfSchwarz* s, const GfCsr* K, void* stream);
+int gf_schwarz_apply(const GfSchwarz* s, const double* r, double* z, int64_t n, void* stream);
+int gf_dot_slot0(int64_t n, const double* x, const double* y, double* partial2, int grid, void* stream);
+
 typedef struct GfPcgWork {
   double* r; double* z; double* p; double* Ap;  /* [n] each */
   double* dinv;       /* [n] inverse diagonal (Jacobi) or 3x3 blocks, see precond */
@@ -184,8 +215,8 @@ typedef struct GfPcgWork {
 } GfPcgWork;
 /* Preconditioned CG on K x = b (K symmetric: nonmatching_opt.py:804-809).
  * Replaces solve_nonmatching_mat(..., 'direct') (utils/opt_utils.py:176,204). */
-int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, double rtol,
-           double atol, int max_it, int check_every, int* iters, double* relres, void* stream);
+int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, const GfSchwarz* precond,
+           double rtol, double atol, int max_it, int check_every, int* iters, double* relres, void* stream);
 int gf_jacobi_setup(const GfCsr* A, double* dinv, void* stream);
 
 /* small vector helpers on device */

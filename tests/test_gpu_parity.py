@@ -98,6 +98,17 @@ def test_baseline_configs_match_goldens(DM, case, gold):
     assert np.linalg.norm(tot.cpu().numpy() - g["dWdt_total"]) < tol * np.linalg.norm(g["dWdt_total"])
 
 
+def test_schwarz_and_jacobi_pcg_agree(DM):
+    """Both preconditioners solve the same system; Schwarz needs far fewer iterations."""
+    pr, kw = cases.slr_small()
+    a, b = DM(pr, precond="schwarz"), DM(pr, precond="jacobi")
+    for dm in (a, b):
+        dm.assemble(residual=True, tangent=True)
+    xa, xb = a.solve(a.R.clone()), b.solve(b.R.clone())
+    assert float(torch.linalg.vector_norm(xa - xb) / torch.linalg.vector_norm(xb)) < 1e-8
+    assert a.last_krylov_its * 20 < b.last_krylov_its
+
+
 def test_bit_reproducible(DM):
     """Colour-ordered scatter + fixed-tree reductions: identical bits run to run."""
     pr, kw = cases.tbeam_small()
@@ -145,9 +156,11 @@ def test_invariants_at_larger_size(DM):
 def test_krylov_error_paths(DM):
     from goldfish_b200 import _capi
     pr, kw = cases.tbeam_small()
-    dm = DM(pr)
+    dm = DM(pr, precond="jacobi")
     dm.assemble(residual=True, tangent=True)
     with pytest.raises(_capi.GoldfishNotConverged):
         dm.solve(dm.R.clone(), max_it=3)
+    with pytest.raises(ValueError):
+        DM(pr, precond="ilu")
     z = dm.solve(torch.zeros_like(dm.R))
     assert float(z.abs().max()) == 0.0
