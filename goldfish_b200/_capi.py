@@ -78,6 +78,11 @@ class GfSchwarz(C.Structure):
                 ("band", c_vp), ("invd", c_vp), ("y", c_vp), ("barrier", c_vp), ("flag", c_vp)]
 
 
+class GfPrecond(C.Structure):
+    _fields_ = [("fine", C.POINTER(GfSchwarz)), ("coarse", C.POINTER(GfSchwarz)), ("P", GfCsr), ("Rt", GfCsr),
+                ("rc", c_vp), ("zc", c_vp), ("bc_c", c_vp), ("n_bc_c", c_i64)]
+
+
 class GfPcgWork(C.Structure):
     _fields_ = [("r", c_vp), ("z", c_vp), ("p", c_vp), ("Ap", c_vp), ("dinv", c_vp),
                 ("scal", c_vp), ("partial", c_vp), ("scal_h", c_vp)]
@@ -94,11 +99,12 @@ SIGNATURES = {
     "gf_mask_vec": [C.POINTER(GfModel), c_vp, c_vp],
     "gf_spmv": [C.POINTER(GfCsr), c_vp, c_vp, c_f64, c_f64, c_vp],
     "gf_spmv_t": [C.POINTER(GfCsr), C.POINTER(GfCsrT), c_vp, c_vp, c_f64, c_f64, c_vp],
-    "gf_pcg": [C.POINTER(GfCsr), c_vp, c_vp, C.POINTER(GfPcgWork), C.POINTER(GfSchwarz), c_f64, c_f64, C.c_int, C.c_int,
+    "gf_pcg": [C.POINTER(GfCsr), c_vp, c_vp, C.POINTER(GfPcgWork), C.POINTER(GfPrecond), c_f64, c_f64, C.c_int, C.c_int,
                C.POINTER(C.c_int), C.POINTER(c_f64), c_vp],
     "gf_schwarz_factor": [C.POINTER(GfSchwarz), C.POINTER(GfCsr), c_vp],
     "gf_schwarz_apply": [C.POINTER(GfSchwarz), c_vp, c_vp, c_i64, c_vp],
     "gf_dot_slot0": [c_i64, c_vp, c_vp, c_vp, C.c_int, c_vp],
+    "gf_precond_apply": [C.POINTER(GfPrecond), c_vp, c_vp, c_i64, c_vp],
     "gf_jacobi_setup": [C.POINTER(GfCsr), c_vp, c_vp],
     "gf_axpby": [c_i64, c_f64, c_vp, c_f64, c_vp, c_vp],
     "gf_dot": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp],

@@ -1,0 +1,60 @@
+"""Coarse spline level of the two-level Schwarz preconditioner (host set-up).
+
+The fine spline space of every patch contains the space on a coarser knot
+vector (a subset of its knots), so the prolongation is exact knot insertion:
+P = kron(P_v, P_u) per patch and field.  The coarse operator is obtained by
+re-discretising the same shells + penalty coupling on the coarse patches with
+the same kernels (a second, small DeviceModel), which keeps everything on the
+GPU and avoids a sparse triple product.
+"""
+import numpy as np
+import scipy.sparse as sp
+from . import bsplines as bsp
+
+
+def _coarse_knots(kn, p, nc):
+    uniq = np.unique(kn)
+    ne = len(uniq) - 1
+    if ne <= nc:
+        return kn.copy(), np.zeros(0)
+    keep = np.unique(np.round(np.linspace(0, ne, nc + 1)).astype(int))
+    interior_keep = uniq[keep[1:-1]]
+    coarse = np.concatenate([np.full(p + 1, uniq[0]), interior_keep, np.full(p + 1, uniq[-1])])
+    missing = np.setdiff1d(uniq[1:-1], interior_keep)
+    return coarse, missing
+
+
+def build(problem, nc=8):
+    """Returns (coarse_problem, P) with P the (N x Nc) scipy CSR prolongation."""
+    patches_c, blocks = [], []
+    for pd in problem["patches"]:
+        p = pd["p"][0]
+        ku, kv = [np.asarray(k, dtype=np.float64) for k in pd["knots"]]
+        n_u, n_v = bsp.num_basis(ku, p), bsp.num_basis(kv, p)
+        cu, mu = _coarse_knots(ku, p, nc); cv, mv = _coarse_knots(kv, p, nc)
+        Pu, ku2 = bsp.knot_insertion_operator(cu, p, mu); Pv, kv2 = bsp.knot_insertion_operator(cv, p, mv)
+        assert np.allclose(ku2, ku) and np.allclose(kv2, kv)
+        X = np.asarray(pd["cp"], dtype=np.float64).reshape(n_v, n_u, 4)
+        # coarse control net: least-squares inverse of the refinement
+        Xc = np.linalg.lstsq(Pv, X.reshape(n_v, -1), rcond=None)[0].reshape(Pv.shape[1], n_u, 4)
+        Xc = np.linalg.lstsq(Pu, Xc.transpose(1, 0, 2).reshape(n_u, -1), rcond=None)[0]
+        Xc = Xc.reshape(Pu.shape[1], Pv.shape[1], 4).transpose(1, 0, 2)
+        nc_u, nc_v = Pu.shape[1], Pv.shape[1]
+        P2 = sp.kron(sp.csr_matrix(Pv), sp.csr_matrix(Pu), format="csr")      # (n_v n_u) x (nc_v nc_u)
+        ncp, ncpc = n_u * n_v, nc_u * nc_v
+        # coarse zero-dofs: a coarse dof is constrained iff its dominant fine dof is
+        bc = np.zeros(3 * ncp, dtype=bool); bc[np.asarray(pd.get("bc_dofs", []), dtype=np.int64)] = True
+        dom = np.asarray(abs(P2).argmax(axis=0)).ravel()
+        bc_c = np.concatenate([f * ncpc + np.nonzero(bc[f * ncp + dom])[0] for f in range(3)])
+        th = pd["thickness"]
+        tval = float(np.mean(np.atleast_1d(th["values"])))
+        patches_c.append(dict(p=pd["p"], knots=(cu, cv), cp=Xc.reshape(-1, 4), bc_dofs=bc_c.astype(np.int64),
+                              quad_deg=pd["quad_deg"], thickness=dict(kind="const", values=tval),
+                              body_force=(0.0, 0.0, 0.0), E=pd.get("E", problem["E"]), nu=pd.get("nu", problem["nu"])))
+        blocks.append(sp.block_diag([P2, P2, P2], format="csr"))
+    coarse = dict(name=problem.get("name", "") + "_coarse", patches=patches_c, E=problem["E"], nu=problem["nu"],
+                  interfaces=problem.get("interfaces", []), penalty_coefficient=problem.get("penalty_coefficient", 1e3),
+                  point_loads=[], edge_loads=[])
+    P = sp.block_diag(blocks, format="csr")
+    P.sort_indices()
+    return coarse, P

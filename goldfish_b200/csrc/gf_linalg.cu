@@ -279,7 +279,26 @@ k_pcg_init_p(int64_t n, const double* z, double* p) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = z[i];
 }
 
-extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, const GfSchwarz* pre,
+__global__ void k_zero_list(const int32_t* list, int64_t n, double* v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[list[i]] = 0.0;
+}
+
+extern "C" int gf_precond_apply(const GfPrecond* pc, const double* r, double* z, int64_t n, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = gf_schwarz_apply(pc->fine, r, z, n, st);
+  if (rc || !pc->coarse) return rc;
+  rc = gf_spmv(&pc->Rt, r, pc->rc, 1.0, 0.0, st);
+  if (rc) return rc;
+  if (pc->n_bc_c > 0) {
+    k_zero_list<<<vec_grid(pc->n_bc_c), RED_THREADS, 0, st>>>(pc->bc_c, pc->n_bc_c, pc->rc);
+    count_launch(1);
+  }
+  rc = gf_schwarz_apply(pc->coarse, pc->rc, pc->zc, pc->Rt.nrows, st);
+  if (rc) return rc;
+  return gf_spmv(&pc->P, pc->zc, z, 1.0, 1.0, st);
+}
+
+extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, const GfPrecond* pre,
                       double rtol, double atol, int max_it, int check_every, int* iters, double* relres,
                       void* stream) {
   if (!A || !b || !x || !w) return set_error(GF_ERR_BADARG, "gf_pcg: null argument");
@@ -291,7 +310,7 @@ extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWor
   if (check_every < 1) check_every = 1;
   k_pcg_init<<<gv, RED_THREADS, 0, st>>>(n, b, w->dinv, x, w->r, w->z, w->p, part2);
   if (pre) {
-    int rc0 = gf_schwarz_apply(pre, w->r, w->z, n, st);
+    int rc0 = gf_precond_apply(pre, w->r, w->z, n, st);
     if (rc0) return rc0;
     k_pcg_rz<<<gv, RED_THREADS, 0, st>>>(n, w->r, w->z, part2);
     k_pcg_init_p<<<gv, RED_THREADS, 0, st>>>(n, w->z, w->p);
@@ -318,7 +337,7 @@ extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWor
     k_pcg_update<<<gv, RED_THREADS, 0, st>>>(n, w->p, w->Ap, w->dinv, x, w->r, w->z, part1, gs, w->scal,
                                              parity, part2);
     if (pre) {
-      int rc1 = gf_schwarz_apply(pre, w->r, w->z, n, st);
+      int rc1 = gf_precond_apply(pre, w->r, w->z, n, st);
       if (rc1) return rc1;
       k_pcg_rz<<<gv, RED_THREADS, 0, st>>>(n, w->r, w->z, part2);
       count_launch(1);

@@ -69,7 +69,7 @@ class DeviceCsr:
 
 class DeviceModel:
     def __init__(self, problem, opt_field=(), shopt_surf_inds=(), device=None, symbolic=None,
-                 precond="schwarz", schwarz_layers=2):
+                 precond="schwarz", schwarz_layers=2, coarse_nc="auto"):
         if not torch.cuda.is_available():
             raise capi.GoldfishError("goldfish_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = capi.load()
@@ -148,6 +148,12 @@ class DeviceModel:
             raise ValueError("Undefined preconditioner: {}".format(precond))
         self.precond = precond
         self.schwarz_layers = schwarz_layers
+        max_ne = max(max(P.neu, P.nev) for P in S.patches)
+        if coarse_nc == "auto":
+            coarse_nc = 0 if max_ne < 16 else (8 if max_ne < 96 else 16)
+        self.coarse_nc = int(coarse_nc) if precond == "schwarz" else 0
+        self.problem = problem
+        self._pc = None
         self._sw = None
         self._sw_factored = False
         self.krylov_rtol = 1e-13
@@ -333,11 +339,39 @@ class DeviceModel:
                                    self._stream()), "gf_dot")
         return float(self.w_scal[8].item())
 
+    def _precond_struct(self):
+        """GfPrecond: fine overlapping blocks (+ coarse spline level)."""
+        if self._pc is None:
+            pc = capi.GfPrecond()
+            pc.fine = C.pointer(self._schwarz())
+            self._coarse = None
+            if self.coarse_nc > 0:
+                from . import coarse as coarse_mod
+                cpr, P = coarse_mod.build(self.problem, nc=self.coarse_nc)
+                cpr["alpha_override"] = self.sym.itf_alpha
+                cm = DeviceModel(cpr, device=self.device, precond="schwarz", coarse_nc=0)
+                cm._single_block = True
+                Pd = DeviceCsr(P.shape[0], P.shape[1], P.indptr, P.indices, self.device)
+                Pd.vals.copy_(torch.from_numpy(P.data))
+                Rt = P.T.tocsr(); Rt.sort_indices()
+                Rd = DeviceCsr(Rt.shape[0], Rt.shape[1], Rt.indptr, Rt.indices, self.device)
+                Rd.vals.copy_(torch.from_numpy(Rt.data))
+                rc = torch.zeros(P.shape[1], dtype=torch.float64, device=self.device)
+                zc = torch.zeros(P.shape[1], dtype=torch.float64, device=self.device)
+                pc.coarse = C.pointer(cm._schwarz())
+                pc.P, pc.Rt = Pd.c_struct(), Rd.c_struct()
+                pc.rc, pc.zc = _ptr(rc), _ptr(zc)
+                pc.bc_c, pc.n_bc_c = _ptr(cm.t["bc_list"]), len(cm.sym.bc_list)
+                self._coarse = (cm, Pd, Rd, rc, zc)
+            self._pc = pc
+        return self._pc
+
     def _schwarz(self):
         """Build (once) the overlapping-Schwarz block structure and its HBM storage."""
         if self._sw is None:
             from .schwarz import SchwarzSetup, NB
-            A = SchwarzSetup(self.sym, layers=self.schwarz_layers).arrays()
+            A = SchwarzSetup(self.sym, layers=self.schwarz_layers,
+                             single_block=getattr(self, "_single_block", False)).arrays()
             dv = self.device
             t = {k: torch.from_numpy(np.ascontiguousarray(A[k])).to(dv)
                  for k in ("n_pad", "nbr", "off_j", "mbj", "rlen", "off_col", "off_y", "off_inv", "glob", "loc", "zptr", "zsrc")}
@@ -367,7 +401,13 @@ class DeviceModel:
         st = self._stream()
         cs = self.K.c_struct()
         if self.precond == "schwarz":
+            pc = self._precond_struct()
             capi.check(self.lib.gf_schwarz_factor(C.byref(self._schwarz()), C.byref(cs), st), "gf_schwarz_factor")
+            if self._coarse is not None:
+                cm = self._coarse[0]
+                cm.assemble(tangent=True)
+                capi.check(self.lib.gf_schwarz_factor(C.byref(cm._schwarz()), C.byref(cm.K.c_struct()), st),
+                           "gf_schwarz_factor(coarse)")
         capi.check(self.lib.gf_jacobi_setup(C.byref(cs), _ptr(self.w_dinv), st), "gf_jacobi_setup")
         self._sw_factored = True
 
@@ -381,7 +421,7 @@ class DeviceModel:
         cs = self.K.c_struct()
         if refactor or not self._sw_factored:
             self.factor_preconditioner()
-        pre = C.byref(self._schwarz()) if self.precond == "schwarz" else None
+        pre = C.byref(self._precond_struct()) if self.precond == "schwarz" else None
         its = C.c_int(0); rel = C.c_double(0.0)
         rc = self.lib.gf_pcg(C.byref(cs), _ptr(b), _ptr(x), C.byref(self.pcg_work), pre,
                              self.krylov_rtol if rtol is None else rtol, 0.0,

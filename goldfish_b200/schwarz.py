@@ -20,7 +20,7 @@ NB = 64
 
 
 class SchwarzSetup:
-    def __init__(self, sym, layers=2):
+    def __init__(self, sym, layers=2, single_block=False):
         S = sym
         self.sym, self.layers = sym, layers
         n_s = S.n_scalar
@@ -40,6 +40,12 @@ class SchwarzSetup:
         cpo = np.array([P.cp_off for P in S.patches])
         Xall = S.cp0[:, :3] / S.cp0[:, 3:4]
         self.blocks = []
+        if single_block:
+            # coarse level: ONE block with every node, reverse Cuthill-McKee ordered
+            from scipy.sparse.csgraph import reverse_cuthill_mckee
+            nodes = np.asarray(reverse_cuthill_mckee(G.astype(np.int32), symmetric_mode=True), dtype=np.int64)
+            self.blocks.append(self._finish_block(nodes, G, n_s, dof, ncp, cpo, n_own=n_s))
+            return
         for P in S.patches:
             own = np.arange(P.cp_off, P.cp_off + P.ncp)
             cur = own
@@ -73,37 +79,40 @@ class SchwarzSetup:
             nodes = np.concatenate([own, extra])
             order = np.lexsort((kf, ks))
             nodes = nodes[order]
-            # node bandwidth from the induced subgraph
-            pos = np.full(n_s, -1, dtype=np.int64); pos[nodes] = np.arange(len(nodes))
-            sub = G[nodes]
-            pr = np.repeat(np.arange(len(nodes)), np.diff(sub.indptr)); pc = pos[sub.indices]
-            ok = pc >= 0
-            beta = int(np.abs(pr[ok] - pc[ok]).max())
-            n = 3 * len(nodes)
-            bw = 3 * beta + 2
-            n_pad = ((n + NB - 1) // NB) * NB
-            nbr_ = n_pad // NB
-            # block-row envelope: first block column reached by each block row
-            # (dof = 3*node + field; fields couple fully, so use node extremes)
-            first_node = np.full(len(nodes), len(nodes), dtype=np.int64)
-            np.minimum.at(first_node, pr[ok], pc[ok])
-            row_blk = (3 * np.arange(len(nodes)) + 2) // NB          # last dof of the node
-            row_blk0 = (3 * np.arange(len(nodes))) // NB             # first dof of the node
-            fc = np.arange(nbr_, dtype=np.int64)
-            np.minimum.at(fc, row_blk, (3 * first_node) // NB)
-            np.minimum.at(fc, row_blk0, (3 * first_node) // NB)
-            for b_ in range(nbr_ - 2, -1, -1):                       # monotone envelope
-                fc[b_] = min(fc[b_], fc[b_ + 1])
-            rlen = np.arange(nbr_) - fc
-            mbj = np.zeros(nbr_, dtype=np.int64)
-            last = np.searchsorted(fc, np.arange(nbr_), side="right") - 1   # last row whose envelope reaches col j
-            mbj = np.maximum(last - np.arange(nbr_), 0)
-            ps = S.scalar_patch[nodes]
-            glob = np.full(n_pad, -1, dtype=np.int32)
-            for f in range(3):
-                glob[f:n:3] = dof[ps] + f * ncp[ps] + (nodes - cpo[ps])
-            self.blocks.append(dict(nodes=nodes, n=n, n_pad=n_pad, bw=bw, nbr=nbr_, mbj=mbj.astype(np.int32),
-                                    rlen=rlen.astype(np.int32), mb=int(mbj.max()), glob=glob, n_own=P.ncp))
+            self.blocks.append(self._finish_block(nodes, G, n_s, dof, ncp, cpo, n_own=P.ncp))
+
+    def _finish_block(self, nodes, G, n_s, dof, ncp, cpo, n_own):
+        """Envelope (variable panel heights) and dof maps of one ordered block."""
+        S = self.sym
+        pos = np.full(n_s, -1, dtype=np.int64); pos[nodes] = np.arange(len(nodes))
+        sub = G[nodes]
+        pr = np.repeat(np.arange(len(nodes)), np.diff(sub.indptr)); pc = pos[sub.indices]
+        ok = pc >= 0
+        beta = int(np.abs(pr[ok] - pc[ok]).max())
+        n = 3 * len(nodes)
+        bw = 3 * beta + 2
+        n_pad = ((n + NB - 1) // NB) * NB
+        nbr_ = n_pad // NB
+        # block-row envelope: first block column reached by each block row
+        # (dof = 3*node + field; fields couple fully, so node extremes suffice)
+        first_node = np.full(len(nodes), len(nodes), dtype=np.int64)
+        np.minimum.at(first_node, pr[ok], pc[ok])
+        row_blk = (3 * np.arange(len(nodes)) + 2) // NB          # block row of the node's last dof
+        row_blk0 = (3 * np.arange(len(nodes))) // NB             # ... and of its first dof
+        fc = np.arange(nbr_, dtype=np.int64)
+        np.minimum.at(fc, row_blk, (3 * first_node) // NB)
+        np.minimum.at(fc, row_blk0, (3 * first_node) // NB)
+        for b_ in range(nbr_ - 2, -1, -1):                       # monotone envelope
+            fc[b_] = min(fc[b_], fc[b_ + 1])
+        rlen = np.arange(nbr_) - fc
+        last = np.searchsorted(fc, np.arange(nbr_), side="right") - 1   # last row whose envelope reaches col j
+        mbj = np.maximum(last - np.arange(nbr_), 0)
+        ps = S.scalar_patch[nodes]
+        glob = np.full(n_pad, -1, dtype=np.int32)
+        for f in range(3):
+            glob[f:n:3] = dof[ps] + f * ncp[ps] + (nodes - cpo[ps])
+        return dict(nodes=nodes, n=n, n_pad=n_pad, bw=bw, nbr=nbr_, mbj=mbj.astype(np.int32),
+                    rlen=rlen.astype(np.int32), mb=int(mbj.max()), glob=glob, n_own=n_own)
 
     def arrays(self):
         """Flat index arrays for GfSchwarz."""

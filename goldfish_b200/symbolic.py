@@ -355,7 +355,9 @@ class Symbolic:
     def _penalty(self):
         ev_lists = {k: [] for k in ("connA", "connB", "connC0", "connC1", "basA", "basB", "basC0", "basC1",
                                     "tpar", "alpha", "dofA", "dofB")}
-        for T in self.itf:
+        self.itf_alpha = []
+        override = self.problem.get("alpha_override")
+        for ii, T in enumerate(self.itf):
             PA, PB = self.patches[T["sA"]], self.patches[T["sB"]]
             c, v = T["c"], T["v"]
             hA, tA = self._size_and_thickness_at(PA, T["xiA"]); hB, tB = self._size_and_thickness_at(PB, T["xiB"])
@@ -363,6 +365,9 @@ class Symbolic:
             ad = np.minimum(self.alpha * PA.E * tA / (h * (1 - PA.nu ** 2)), self.alpha * PB.E * tB / (h * (1 - PB.nu ** 2)))
             ar = np.minimum(self.alpha * PA.E * tA ** 3 / (12 * h * (1 - PA.nu ** 2)),
                             self.alpha * PB.E * tB ** 3 / (12 * h * (1 - PB.nu ** 2)))
+            if override is not None:       # coarse level of the preconditioner: keep the fine penalty stiffness
+                ad, ar = override[ii]
+            self.itf_alpha.append((ad, ar))
             n = len(v)
             ev_lists["connA"].append(PA.cp_off + T["connA"][v]); ev_lists["connB"].append(PB.cp_off + T["connB"][v])
             ev_lists["connC0"].append(PA.cp_off + T["connA"][c]); ev_lists["connC1"].append(PA.cp_off + T["connA"][c + 1])

@@ -206,6 +206,20 @@ int gf_schwarz_factor(const GfSchwarz* s, const GfCsr* K, void* stream);
 int gf_schwarz_apply(const GfSchwarz* s, const double* r, double* z, int64_t n, void* stream);
 int gf_dot_slot0(int64_t n, const double* x, const double* y, double* partial2, int grid, void* stream);
 
+/* Two-level preconditioner  z = sum_i R_i^T A_i^-1 R_i r  +  P Kc^-1 P^T r :
+ * `fine` = overlapping patch blocks, `coarse` = ONE block holding the factor of
+ * the coarse-spline operator (same shells + coupling re-discretised on a coarser
+ * knot vector by the same kernels), P = knot-insertion prolongation, Rt = P^T. */
+typedef struct GfPrecond {
+  const GfSchwarz* fine;
+  const GfSchwarz* coarse;        /* may be NULL: one-level                           */
+  GfCsr P, Rt;
+  double* rc; double* zc;         /* [Nc] work vectors                                */
+  const int32_t* bc_c;            /* coarse zero-dofs                                 */
+  int64_t n_bc_c;
+} GfPrecond;
+int gf_precond_apply(const GfPrecond* pc, const double* r, double* z, int64_t n, void* stream);
+
 typedef struct GfPcgWork {
   double* r; double* z; double* p; double* Ap;  /* [n] each */
   double* dinv;       /* [n] inverse diagonal (Jacobi) or 3x3 blocks, see precond */
@@ -215,7 +229,7 @@ typedef struct GfPcgWork {
 } GfPcgWork;
 /* Preconditioned CG on K x = b (K symmetric: nonmatching_opt.py:804-809).
  * Replaces solve_nonmatching_mat(..., 'direct') (utils/opt_utils.py:176,204). */
-int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, const GfSchwarz* precond,
+int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, const GfPrecond* precond,
            double rtol, double atol, int max_it, int check_every, int* iters, double* relres, void* stream);
 int gf_jacobi_setup(const GfCsr* A, double* dinv, void* stream);
 

@@ -5,16 +5,16 @@ import numpy as np, torch
 from goldfish_b200 import problems
 from goldfish_b200.device_model import DeviceModel
 
-def run(name, pr, oracle=True):
-    dm = DeviceModel(pr, precond="schwarz")
+def run(name, pr, oracle=True, **kw):
+    dm = DeviceModel(pr, precond="schwarz", **kw)
     dm.u.zero_(); dm.assemble(residual=True, tangent=True)
     rhs = -dm.R.clone()
     torch.cuda.synchronize(); t0 = time.time()
     dm.factor_preconditioner(); torch.cuda.synchronize(); t1 = time.time()
     x = dm.solve(rhs); torch.cuda.synchronize(); t2 = time.time()
     A = dm._sw[3]
-    msg = "%s N=%d blocks=%d max_nbr=%d max_mb=%d band=%.2f GB | factor %.3fs solve %.3fs its=%d relres=%.2e" % (
-        name, dm.sym.N, A["nblocks"], A["max_nbr"], A["max_mb"], A["band_len"] * 8 / 1e9, t1 - t0, t2 - t1, dm.last_krylov_its, dm.last_relres)
+    msg = "%s nc=%d N=%d blocks=%d max_nbr=%d max_mb=%d band=%.2f GB | factor %.3fs solve %.3fs its=%d relres=%.2e" % (
+        name, dm.coarse_nc, dm.sym.N, A["nblocks"], A["max_nbr"], A["max_mb"], A["band_len"] * 8 / 1e9, t1 - t0, t2 - t1, dm.last_krylov_its, dm.last_relres)
     if oracle:
         from oracle.model import OracleModel
         om = OracleModel(pr); K = om.stiffness(); xo = om.solve(K, -om.residual())
@@ -31,7 +31,8 @@ if __name__ == "__main__":
     run("slr4", problems.scordelis_lo(num_el=4))
     run("plate", problems.plate(os.path.join(os.path.dirname(__file__), "..", "tests/golden/plate_c1_input.npz")))
     for ne in sizes:
-        t0 = time.time(); pr = problems.cylinder(n_el=ne); 
-        dm = run("cyl%d" % ne, pr, oracle=(ne <= 8))
-        dm.newton(verbose=True)
-        print("   newton kits", dm.newton_krylov_its, "setup+run wall", time.time() - t0, flush=True)
+        for nc in (0, 8, 16):
+            t0 = time.time(); pr = problems.cylinder(n_el=ne)
+            dm = run("cyl%d" % ne, pr, oracle=(ne <= 8), coarse_nc=nc)
+            print("   setup+run wall", time.time() - t0, flush=True)
+            del dm; torch.cuda.empty_cache()
