@@ -38,7 +38,9 @@ k_sw_fill(GfSchwarz S, GfCsr K) {
   const int lr = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (lr >= S.n_pad[i]) return;
   const int32_t* glob = S.glob + S.off_y[i];
-  const int32_t* loc = S.loc + (size_t)i * K.nrows;
+  const int32_t* gs = S.gs + S.off_g[i];
+  const int32_t* ls = S.ls + S.off_g[i];
+  const int ng = (int)(S.off_g[i + 1] - S.off_g[i]);
   const int r = glob[lr];
   const int br = lr / NB, rr = lr % NB;
   if (r < 0) {  // padding dof: identity
@@ -46,35 +48,30 @@ k_sw_fill(GfSchwarz S, GfCsr K) {
     return;
   }
   for (int64_t k = K.indptr[r] + lane; k < K.indptr[r + 1]; k += 32) {
-    const int lc = loc[K.indices[k]];
-    if (lc < 0 || lc > lr) continue;
+    // global column -> local index of this block (binary search in the sorted dof list)
+    const int c = K.indices[k];
+    int lo = 0, hi = ng;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (gs[mid] < c) lo = mid + 1; else hi = mid; }
+    if (lo >= ng || gs[lo] != c) continue;
+    const int lc = ls[lo];
+    if (lc > lr) continue;
     const int bj = lc / NB, cc = lc % NB;
     sw_block(S, i, bj, br - bj)[rr * NB + cc] = K.vals[k];
   }
 }
 
-// ---- diagonal block: Cholesky + inverse of the factor -------------------------
-__global__ void __launch_bounds__(256)
-k_sw_potrf(GfSchwarz S, int j) {
-  const int i = blockIdx.y;
-  if (j >= S.nbr[i]) return;
-  extern __shared__ double sm[];
-  double (*A)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
-  double (*Li)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm + NB * (NB + 1));
-  double* blk = sw_block(S, i, j, 0);
+// ---- in-shared-memory Cholesky of a 64 x 64 block (lower), all 256 threads ------
+__device__ __forceinline__ void chol64(double (*A)[NB + 1], int32_t* flag) {
   const int tid = threadIdx.x;
-  for (int e = tid; e < NB2; e += 256) { A[e / NB][e % NB] = blk[e]; Li[e / NB][e % NB] = 0.0; }
-  __syncthreads();
   for (int c = 0; c < NB; ++c) {
     if (tid == 0) {
       const double d = A[c][c];
-      if (!(d > 0.0)) { atomicExch(S.flag, 1); A[c][c] = 1.0; } else A[c][c] = sqrt(d);
+      if (!(d > 0.0)) { atomicExch(flag, 1); A[c][c] = 1.0; } else A[c][c] = sqrt(d);
     }
     __syncthreads();
     const double inv = 1.0 / A[c][c];
-    for (int r = c + 1 + tid; r < NB; r += 256) A[r][c] *= inv;
+    if (tid > c && tid < NB) A[tid][c] *= inv;
     __syncthreads();
-    // trailing update of the lower triangle
     const int m = NB - c - 1;
     for (int e = tid; e < m * m; e += 256) {
       const int r = c + 1 + e / m, cc = c + 1 + e % m;
@@ -82,54 +79,71 @@ k_sw_potrf(GfSchwarz S, int j) {
     }
     __syncthreads();
   }
-  // inverse of L: thread t solves L x = e_t
-  if (tid < NB) {
+}
+
+// ---- panel step j: every CTA factors the diagonal block itself (redundantly, it
+// is tiny) and CTA k >= 1 solves its block  B_k <- B_k L_jj^-T  by substitution.
+// One launch per step instead of potrf -> trsm.
+__global__ void __launch_bounds__(256)
+k_sw_panel(GfSchwarz S, int j) {
+  const int i = blockIdx.y, k = blockIdx.x;
+  if (j >= S.nbr[i] || k > sw_mb(S, i, j)) return;
+  extern __shared__ double sm[];
+  double (*A)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
+  double (*B)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm + NB * (NB + 1));
+  double* dblk = sw_block(S, i, j, 0);
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB2; e += 256) A[e / NB][e % NB] = dblk[e];
+  double* blk = sw_block(S, i, j, k);
+  if (k > 0) for (int e = tid; e < NB2; e += 256) B[e / NB][e % NB] = blk[e];
+  __syncthreads();
+  chol64(A, S.flag);
+  if (k == 0) {
+    // L_jj goes to the invd slot (inverted in place later); the band keeps A_jj so that
+    // the other CTAs of this launch, which may start later, still read the unfactored block
+    double* Lout = S.invd + S.off_inv[i] + (size_t)j * NB2;
+    for (int e = tid; e < NB2; e += 256) { const int r = e / NB, c = e % NB; Lout[e] = (c <= r) ? A[r][c] : 0.0; }
+    return;
+  }
+  // X L^T = B  =>  X[r][c] = (B[r][c] - sum_{m<c} X[r][m] L[c][m]) / L[c][c]; 4 threads per row
+  const int r = tid >> 2, q = tid & 3;
+  for (int c = 0; c < NB; ++c) {
+    double sdot = 0.0;
+    for (int m = q; m < c; m += 4) sdot = fma(B[r][m], A[c][m], sdot);
+    sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+    sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+    if (q == 0) B[r][c] = (B[r][c] - sdot) / A[c][c];
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int e = tid; e < NB2; e += 256) blk[e] = B[e / NB][e % NB];
+}
+
+// ---- inverse of every diagonal factor block (off the critical path) -----------
+__global__ void __launch_bounds__(256)
+k_sw_invert(GfSchwarz S) {
+  const int i = blockIdx.y, j = blockIdx.x;
+  if (j >= S.nbr[i]) return;
+  extern __shared__ double sm[];
+  double (*A)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
+  double (*Li)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm + NB * (NB + 1));
+  double* inv = S.invd + S.off_inv[i] + (size_t)j * NB2;     // holds L_jj on entry
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB2; e += 256) { A[e / NB][e % NB] = inv[e]; Li[e / NB][e % NB] = 0.0; }
+  __syncthreads();
+  if (tid < NB) {          // thread t solves L x = e_t
     const int t = tid;
     Li[t][t] = 1.0 / A[t][t];
     for (int r = t + 1; r < NB; ++r) {
-      double s = 0.0;
-      for (int m = t; m < r; ++m) s = fma(A[r][m], Li[m][t], s);
-      Li[r][t] = -s / A[r][r];
+      double s0 = 0.0, s1 = 0.0;
+      int m = t;
+      for (; m + 1 < r; m += 2) { s0 = fma(A[r][m], Li[m][t], s0); s1 = fma(A[r][m + 1], Li[m + 1][t], s1); }
+      if (m < r) s0 = fma(A[r][m], Li[m][t], s0);
+      Li[r][t] = -(s0 + s1) / A[r][r];
     }
   }
   __syncthreads();
-  double* inv = S.invd + S.off_inv[i] + (size_t)j * NB2;
-  for (int e = tid; e < NB2; e += 256) {
-    const int r = e / NB, c = e % NB;
-    blk[e] = (c <= r) ? A[r][c] : 0.0;
-    inv[e] = (c <= r) ? Li[r][c] : 0.0;
-  }
-}
-
-// ---- panel: B_k <- B_k L_jj^-T ---------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_sw_trsm(GfSchwarz S, int j) {
-  const int i = blockIdx.y, k = blockIdx.x + 1;
-  if (j >= S.nbr[i] || k > sw_mb(S, i, j)) return;
-  extern __shared__ double sm[];
-  double (*B)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
-  double (*Li)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm + NB * (NB + 1));
-  double* blk = sw_block(S, i, j, k);
-  const double* inv = S.invd + S.off_inv[i] + (size_t)j * NB2;
-  const int tid = threadIdx.x;
-  for (int e = tid; e < NB2; e += 256) { B[e / NB][e % NB] = blk[e]; Li[e / NB][e % NB] = inv[e]; }
-  __syncthreads();
-  // out[r][c] = sum_{m<=c} B[r][m] Linv[c][m]
-  const int r0 = (tid / 16) * 4, c0 = (tid % 16) * 4;
-  double acc[4][4] = {};
-  for (int m = 0; m < NB; ++m) {
-    double a[4], b[4];
-#pragma unroll
-    for (int x = 0; x < 4; ++x) { a[x] = B[r0 + x][m]; b[x] = Li[c0 + x][m]; }
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-      for (int y = 0; y < 4; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
-  }
-#pragma unroll
-  for (int x = 0; x < 4; ++x)
-#pragma unroll
-    for (int y = 0; y < 4; ++y) blk[(r0 + x) * NB + c0 + y] = acc[x][y];
+  for (int e = tid; e < NB2; e += 256) { const int r = e / NB, c = e % NB; inv[e] = (c <= r) ? Li[r][c] : 0.0; }
 }
 
 // ---- trailing update: A(j+k1, j+k2) -= B_k1 B_k2^T ------------------------------
@@ -197,71 +211,143 @@ __device__ __forceinline__ void group_barrier(unsigned* cnt, unsigned target) {
   __syncthreads();
 }
 
-// y_blk (64) <- M y_blk with M = Linv (forward) or Linv^T (backward); result in xs (smem)
-__device__ __forceinline__ void diag_apply(const double* __restrict__ inv, const double* ys, double* xs, bool transpose) {
-  // 256 threads: 4 threads per row
-  const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
-  double s = 0.0;
-  if (!transpose) {
-    for (int c = q; c <= r; c += 4) s = fma(inv[r * NB + c], ys[c], s);
-  } else {
-    for (int c = r + q; c < NB; c += 4) s = fma(inv[c * NB + r], ys[c], s);
+// ---- after the factorisation: turn the factor into "solve form" -----------------
+//   M(j+k, j) = L(j+k, j) L_jj^-1        (k >= 1)
+//   D_j       = L_jj^-T L_jj^-1 = (A_jj - ...)^-1
+// so that the triangular sweeps need no diagonal solve inside their dependency
+// chain:  forward  y_{j+k} -= M(j+k,j) y_j ;  w_j = D_j y_j (parallel) ;
+//         backward x_j = w_j - s_j,  s_{j-k} += M(j,j-k)^T x_j.
+__global__ void __launch_bounds__(256)
+k_sw_convert_panel(GfSchwarz S) {
+  const int i = blockIdx.z, j = blockIdx.y, k = blockIdx.x + 1;
+  if (j >= S.nbr[i] || k > sw_mb(S, i, j)) return;
+  extern __shared__ double sm[];
+  double (*B)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
+  double (*Li)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm + NB * (NB + 1));
+  double* blk = sw_block(S, i, j, k);
+  const double* inv = S.invd + S.off_inv[i] + (size_t)j * NB2;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB2; e += 256) { B[e / NB][e % NB] = blk[e]; Li[e % NB][e / NB] = inv[e]; }  // Li transposed
+  __syncthreads();
+  // out[r][c] = sum_m B[r][m] Linv[m][c] = sum_m B[r][m] LiT[c][m]
+  const int r0 = (tid / 16) * 4, c0 = (tid % 16) * 4;
+  double acc[4][4] = {};
+  for (int m = 0; m < NB; ++m) {
+    double a[4], b[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) { a[x] = B[r0 + x][m]; b[x] = Li[c0 + x][m]; }
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
   }
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  if (q == 0) xs[r] = s;
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) blk[(r0 + x) * NB + c0 + y] = acc[x][y];
 }
 
 __global__ void __launch_bounds__(256)
-k_sw_solve(GfSchwarz S, int G) {
-  const int i = blockIdx.x / G, cta = blockIdx.x % G;
-  __shared__ double ys[NB], xs[NB];
+k_sw_convert_diag(GfSchwarz S) {
+  const int i = blockIdx.y, j = blockIdx.x;
+  if (j >= S.nbr[i]) return;
+  extern __shared__ double sm[];
+  double (*Li)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
+  double* inv = S.invd + S.off_inv[i] + (size_t)j * NB2;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB2; e += 256) Li[e / NB][e % NB] = inv[e];
+  __syncthreads();
+  // D[r][c] = sum_m Linv[m][r] Linv[m][c],  m >= max(r, c)
+  const int r0 = (tid / 16) * 4, c0 = (tid % 16) * 4;
+  double acc[4][4] = {};
+  for (int m = 0; m < NB; ++m) {
+    double a[4], b[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) { a[x] = Li[m][r0 + x]; b[x] = Li[m][c0 + x]; }
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) inv[(r0 + x) * NB + c0 + y] = acc[x][y];
+}
+
+// one block GEMV of the forward sweep with the block already in registers:
+// warp w owns rows 8w..8w+7, lanes run along the row (coalesced 512-B rows)
+__device__ __forceinline__ void load_blk(const double* __restrict__ L, int w, int lane, double (&Lr)[16]) {
+  const double* p = L + (size_t)(w * 8) * NB;
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) { Lr[2 * rr] = __ldcs(p + rr * NB + lane); Lr[2 * rr + 1] = __ldcs(p + rr * NB + lane + 32); }
+}
+
+__global__ void __launch_bounds__(256)
+k_sw_solve(GfSchwarz S, int G, int first_block) {
+  const int i = first_block + blockIdx.x / G, cta = blockIdx.x % G;
+  __shared__ double xs[NB];
   __shared__ double red[8][NB];
   const int nbr = S.nbr[i];
   const int32_t* mbj = S.mbj + S.off_j[i];
   const int32_t* rlen = S.rlen + S.off_j[i];
   double* y = S.y + S.off_y[i];
+  double* sv = S.s + S.off_y[i];
   const double* invd = S.invd + S.off_inv[i];
   unsigned* cnt = S.barrier + i;
   unsigned step = 0;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  // forward: L x = y
+  double Lr[16];
+  const int k0 = 1 + cta;
+
+  // ---------------- forward: y_{j+k} -= M(j+k, j) y_j ----------------
+  bool have = (nbr > 0 && k0 <= mbj[0]);
+  if (have) load_blk(sw_block(S, i, 0, k0), w, lane, Lr);
   for (int j = 0; j < nbr; ++j) {
-    if (tid < NB) ys[tid] = __ldcg(y + (size_t)j * NB + tid);
-    __syncthreads();
-    diag_apply(invd + (size_t)j * NB2, ys, xs, false);
-    __syncthreads();
-    if (cta == 0 && tid < NB) __stcg(y + (size_t)j * NB + tid, xs[tid]);
-    const double x0 = xs[lane], x1 = xs[lane + 32];
-    for (int k = 1 + cta; k <= mbj[j]; k += G) {
-      // y_{j+k} -= L(j+k,j) x_j : warp w owns rows 8w..8w+7, lanes run along the row (coalesced)
-      const double* L = sw_block(S, i, j, k) + (size_t)(w * 8) * NB;
-      double s[8];
+    const double x0 = __ldcg(y + (size_t)j * NB + lane), x1 = __ldcg(y + (size_t)j * NB + lane + 32);
+    for (int k = k0; k <= mbj[j]; k += G) {
+      if (k != k0) load_blk(sw_block(S, i, j, k), w, lane, Lr);
+      double sacc[8];
 #pragma unroll
-      for (int rr = 0; rr < 8; ++rr) s[rr] = __ldcs(L + rr * NB + lane) * x0 + __ldcs(L + rr * NB + lane + 32) * x1;
-#pragma unroll
-      for (int rr = 0; rr < 8; ++rr) s[rr] = warp_sum(s[rr]);
+      for (int rr = 0; rr < 8; ++rr) sacc[rr] = warp_sum(Lr[2 * rr] * x0 + Lr[2 * rr + 1] * x1);
       if (lane < 8) {
-        double v = s[0];
+        double v = sacc[0];
 #pragma unroll
-        for (int rr = 1; rr < 8; ++rr) v = (lane == rr) ? s[rr] : v;
+        for (int rr = 1; rr < 8; ++rr) v = (lane == rr) ? sacc[rr] : v;
         double* dst = y + (size_t)(j + k) * NB + w * 8 + lane;
         __stcg(dst, __ldcg(dst) - v);
       }
     }
+    // prefetch the first block of the next step while waiting at the barrier
+    if (j + 1 < nbr && k0 <= mbj[j + 1]) load_blk(sw_block(S, i, j + 1, k0), w, lane, Lr);
     ++step;
     group_barrier(cnt, step * (unsigned)G);
   }
-  // backward: L^T x = y
+  // ---------------- diagonal: w_j = D_j y_j ; s = 0 ----------------
+  for (int j = cta; j < nbr; j += G) {
+    if (tid < NB) xs[tid] = __ldcg(y + (size_t)j * NB + tid);
+    __syncthreads();
+    const double* D = invd + (size_t)j * NB2 + (size_t)(w * 8) * NB;
+    double sacc[8];
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) sacc[rr] = warp_sum(D[rr * NB + lane] * xs[lane] + D[rr * NB + lane + 32] * xs[lane + 32]);
+    __syncthreads();
+    if (lane < 8) {
+      double v = sacc[0];
+#pragma unroll
+      for (int rr = 1; rr < 8; ++rr) v = (lane == rr) ? sacc[rr] : v;
+      __stcg(y + (size_t)j * NB + w * 8 + lane, v);
+      __stcg(sv + (size_t)j * NB + w * 8 + lane, 0.0);
+    }
+  }
+  ++step;
+  group_barrier(cnt, step * (unsigned)G);
+  // ---------------- backward: x_j = w_j - s_j ; s_{j-k} += M(j, j-k)^T x_j ----------------
   for (int j = nbr - 1; j >= 0; --j) {
-    if (tid < NB) ys[tid] = __ldcg(y + (size_t)j * NB + tid);
+    if (tid < NB) xs[tid] = __ldcg(y + (size_t)j * NB + tid) - __ldcg(sv + (size_t)j * NB + tid);
     __syncthreads();
-    diag_apply(invd + (size_t)j * NB2, ys, xs, true);
-    __syncthreads();
-    if (cta == 0 && tid < NB) __stcg(y + (size_t)j * NB + tid, xs[tid]);
-    for (int k = 1 + cta; k <= rlen[j]; k += G) {
-      // y_{j-k} -= L(j, j-k)^T x_j ; block (row j, col j-k) is panel j-k, offset k.
-      // warp w sums its 8 rows for columns lane, lane+32; then the 8 warps are combined.
+    for (int k = k0; k <= rlen[j]; k += G) {
       const double* L = sw_block(S, i, j - k, k) + (size_t)(w * 8) * NB;
       double a0 = 0.0, a1 = 0.0;
 #pragma unroll
@@ -277,12 +363,15 @@ k_sw_solve(GfSchwarz S, int G) {
         double v = 0.0;
 #pragma unroll
         for (int ww = 0; ww < 8; ++ww) v += red[ww][tid];
-        double* dst = y + (size_t)(j - k) * NB + tid;
-        __stcg(dst, __ldcg(dst) - v);
+        double* dst = sv + (size_t)(j - k) * NB + tid;
+        __stcg(dst, __ldcg(dst) + v);
       }
     }
     ++step;
     group_barrier(cnt, step * (unsigned)G);
+    // everyone has read w_j and s_j: the final x_j can now replace w_j
+    if (cta == 0 && tid < NB) __stcg(y + (size_t)j * NB + tid, xs[tid]);
+    __syncthreads();
   }
 }
 
@@ -317,18 +406,22 @@ extern "C" int gf_schwarz_factor(const GfSchwarz* S, const GfCsr* K, void* strea
   k_sw_fill<<<gf, 256, 0, st>>>(*S, *K);
   const size_t smem = 2 * NB * (NB + 1) * sizeof(double);
   e = cudaFuncSetAttribute(k_sw_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_potrf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(k_sw_*)");
   for (int j = 0; j < S->max_nbr; ++j) {
-    k_sw_potrf<<<dim3(1, S->nblocks), 256, smem, st>>>(*S, j);
     const int m = S->step_mb_h[j];      // tallest panel of this step over all patch blocks
-    if (m > 0) {
-      k_sw_trsm<<<dim3(m, S->nblocks), 256, smem, st>>>(*S, j);
-      k_sw_update<<<dim3(m * (m + 1) / 2, S->nblocks), 256, smem, st>>>(*S, j);
-    }
-    count_launch(3);
+    k_sw_panel<<<dim3(m + 1, S->nblocks), 256, smem, st>>>(*S, j);
+    if (m > 0) k_sw_update<<<dim3(m * (m + 1) / 2, S->nblocks), 256, smem, st>>>(*S, j);
+    count_launch(2);
   }
+  e = cudaFuncSetAttribute(k_sw_convert_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_convert_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(k_sw_convert)");
+  k_sw_invert<<<dim3(S->max_nbr, S->nblocks), 256, smem, st>>>(*S);
+  if (S->max_mb > 0) k_sw_convert_panel<<<dim3(S->max_mb, S->max_nbr, S->nblocks), 256, smem, st>>>(*S);
+  k_sw_convert_diag<<<dim3(S->max_nbr, S->nblocks), 256, smem, st>>>(*S);
+  count_launch(2);
   int flag = 0;
   e = cudaMemcpyAsync(&flag, S->flag, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -344,10 +437,29 @@ extern "C" int gf_schwarz_apply(const GfSchwarz* S, const double* r, double* z, 
   cudaError_t e = cudaMemsetAsync(S->barrier, 0, sizeof(unsigned) * S->nblocks, st);
   if (e != cudaSuccess) return set_cuda_error(e, "gf_schwarz_apply memset");
   GfSchwarz Sv = *S;
-  int G = S->ctas_per_block;
-  void* args[] = {&Sv, &G};
-  e = cudaLaunchCooperativeKernel((void*)k_sw_solve, dim3(S->nblocks * G), dim3(256), args, 0, st);
-  if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchCooperativeKernel(k_sw_solve)");
+  static int sms = 0, occ = 0;
+  if (!sms) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sw_solve, 256, 0);
+    if (occ > 2) occ = 2;
+    if (occ < 1) occ = 1;
+  }
+  const int cap = sms * occ;                   // all CTAs of one launch must be co-resident
+  int G = cap / S->nblocks;
+  if (G > S->max_mb) G = S->max_mb;            // one panel block per CTA and step is enough
+  if (S->ctas_per_block > 0 && G > S->ctas_per_block) G = S->ctas_per_block;
+  if (G < 1) G = 1;
+  const int per_launch = cap / G;              // patch blocks per cooperative launch
+  for (int b0 = 0; b0 < S->nblocks; b0 += per_launch) {
+    int nb_l = S->nblocks - b0; if (nb_l > per_launch) nb_l = per_launch;
+    int first = b0;
+    void* args[] = {&Sv, &G, &first};
+    e = cudaLaunchCooperativeKernel((void*)k_sw_solve, dim3(nb_l * G), dim3(256), args, 0, st);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchCooperativeKernel(k_sw_solve)");
+    count_launch(1);
+  }
+  count_launch(-1);
   int g2 = (int)((n + 255) / 256); if (g2 > 2048) g2 = 2048;
   k_sw_gather_out<<<g2, 256, 0, st>>>(*S, z, n);
   count_launch(2);

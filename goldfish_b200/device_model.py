@@ -69,7 +69,7 @@ class DeviceCsr:
 
 class DeviceModel:
     def __init__(self, problem, opt_field=(), shopt_surf_inds=(), device=None, symbolic=None,
-                 precond="schwarz", schwarz_layers=2, coarse_nc="auto"):
+                 precond="schwarz", schwarz_layers=2, coarse_nc="auto", schwarz_sub=64):
         if not torch.cuda.is_available():
             raise capi.GoldfishError("goldfish_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = capi.load()
@@ -148,9 +148,10 @@ class DeviceModel:
             raise ValueError("Undefined preconditioner: {}".format(precond))
         self.precond = precond
         self.schwarz_layers = schwarz_layers
+        self.schwarz_sub = schwarz_sub
         max_ne = max(max(P.neu, P.nev) for P in S.patches)
         if coarse_nc == "auto":
-            coarse_nc = 0 if max_ne < 16 else (8 if max_ne < 96 else 16)
+            coarse_nc = 0 if max_ne < 16 else int(min(24, max(8, max_ne // 8)))
         self.coarse_nc = int(coarse_nc) if precond == "schwarz" else 0
         self.problem = problem
         self._pc = None
@@ -370,27 +371,25 @@ class DeviceModel:
         """Build (once) the overlapping-Schwarz block structure and its HBM storage."""
         if self._sw is None:
             from .schwarz import SchwarzSetup, NB
-            A = SchwarzSetup(self.sym, layers=self.schwarz_layers,
+            A = SchwarzSetup(self.sym, layers=self.schwarz_layers, sub=self.schwarz_sub,
                              single_block=getattr(self, "_single_block", False)).arrays()
             dv = self.device
             t = {k: torch.from_numpy(np.ascontiguousarray(A[k])).to(dv)
-                 for k in ("n_pad", "nbr", "off_j", "mbj", "rlen", "off_col", "off_y", "off_inv", "glob", "loc", "zptr", "zsrc")}
+                 for k in ("n_pad", "nbr", "off_j", "mbj", "rlen", "off_col", "off_y", "off_inv", "glob", "gs", "ls", "off_g", "zptr", "zsrc")}
             t["band"] = torch.zeros(A["band_len"], dtype=torch.float64, device=dv)
             t["invd"] = torch.zeros(A["inv_len"], dtype=torch.float64, device=dv)
             t["y"] = torch.zeros(A["n_y"], dtype=torch.float64, device=dv)
+            t["s"] = torch.zeros(A["n_y"], dtype=torch.float64, device=dv)
             t["barrier"] = torch.zeros(A["nblocks"], dtype=torch.int32, device=dv)
             t["flag"] = torch.zeros(1, dtype=torch.int32, device=dv)
             step_mb = np.ascontiguousarray(A["step_mb"], dtype=np.int32)
             s = capi.GfSchwarz()
             s.nblocks, s.nb = A["nblocks"], NB
             s.max_nbr, s.max_mb, s.max_n_pad = A["max_nbr"], A["max_mb"], A["max_n_pad"]
-            sms = torch.cuda.get_device_properties(dv).multi_processor_count
-            if A["nblocks"] > sms:
-                raise capi.GoldfishError("more Schwarz blocks (patches) than SMs: not supported by the cooperative solve")
-            s.ctas_per_block = max(1, min(32, sms // A["nblocks"]))
+            s.ctas_per_block = 0          # chosen in gf_schwarz_apply from the SM count and panel height
             s.n_y, s.band_len = A["n_y"], A["band_len"]
-            for k in ("n_pad", "nbr", "off_j", "mbj", "rlen", "off_col", "off_y", "off_inv", "glob", "loc", "zptr", "zsrc",
-                      "band", "invd", "y", "barrier", "flag"):
+            for k in ("n_pad", "nbr", "off_j", "mbj", "rlen", "off_col", "off_y", "off_inv", "glob", "gs", "ls", "off_g", "zptr", "zsrc",
+                      "band", "invd", "y", "s", "barrier", "flag"):
                 setattr(s, k, _ptr(t[k]))
             s.step_mb_h = step_mb.ctypes.data_as(C.c_void_p)
             self._sw = (s, t, step_mb, A)

@@ -20,7 +20,7 @@ NB = 64
 
 
 class SchwarzSetup:
-    def __init__(self, sym, layers=2, single_block=False):
+    def __init__(self, sym, layers=2, single_block=False, sub=48):
         S = sym
         self.sym, self.layers = sym, layers
         n_s = S.n_scalar
@@ -46,26 +46,32 @@ class SchwarzSetup:
             nodes = np.asarray(reverse_cuthill_mckee(G.astype(np.int32), symmetric_mode=True), dtype=np.int64)
             self.blocks.append(self._finish_block(nodes, G, n_s, dof, ncp, cpo, n_own=n_s))
             return
-        for P in S.patches:
-            own = np.arange(P.cp_off, P.cp_off + P.ncp)
+        self.sub = sub
+        for P, (i0, i1, j0, j1) in self._subdomains(S.patches, sub):
+            # own set = a rectangle of the patch's CP grid (sub x sub nodes at most):
+            # short band => short triangular-solve chains and cheap factorisation;
+            # the coarse spline level carries the global coupling.
+            II, JJ = np.meshgrid(np.arange(i0, i1), np.arange(j0, j1), indexing="xy")
+            own = (P.cp_off + II + JJ * P.n_u).ravel()
             cur = own
             for _ in range(layers):
                 cur = np.union1d(cur, G[cur].indices)
             extra = np.setdiff1d(cur, own)
             # natural keys of own nodes; slow direction = the one with more CPs
-            I = (own - P.cp_off) % P.n_u; J = (own - P.cp_off) // P.n_u
-            swap = P.n_u > P.n_v
+            I = (own - P.cp_off) % P.n_u - i0; J = (own - P.cp_off) // P.n_u - j0
+            nru, nrv = i1 - i0, j1 - j0
+            swap = nru > nrv
             slow_own, fast_own = (I, J) if swap else (J, I)
             ks, kf = slow_own.astype(np.float64), fast_own.astype(np.float64)
             if len(extra):
-                Xo = Xall[own].reshape(P.n_v, P.n_u, 3)
+                Xo = Xall[own].reshape(nrv, nru, 3)
                 tree = cKDTree(Xall[own])
                 _, nn = tree.query(Xall[extra])
                 In, Jn = I[nn], J[nn]
 
                 def direction(di, dj):
-                    a_i = np.clip(In + di, 0, P.n_u - 1); a_j = np.clip(Jn + dj, 0, P.n_v - 1)
-                    b_i = np.clip(In - di, 0, P.n_u - 1); b_j = np.clip(Jn - dj, 0, P.n_v - 1)
+                    a_i = np.clip(In + di, 0, nru - 1); a_j = np.clip(Jn + dj, 0, nrv - 1)
+                    b_i = np.clip(In - di, 0, nru - 1); b_j = np.clip(Jn - dj, 0, nrv - 1)
                     d = Xo[a_j, a_i] - Xo[b_j, b_i]
                     steps = (a_i - b_i) + (a_j - b_j)
                     h = np.linalg.norm(d, axis=1) / np.maximum(steps, 1)
@@ -79,7 +85,17 @@ class SchwarzSetup:
             nodes = np.concatenate([own, extra])
             order = np.lexsort((kf, ks))
             nodes = nodes[order]
-            self.blocks.append(self._finish_block(nodes, G, n_s, dof, ncp, cpo, n_own=P.ncp))
+            self.blocks.append(self._finish_block(nodes, G, n_s, dof, ncp, cpo, n_own=len(own)))
+
+    @staticmethod
+    def _subdomains(patches, sub):
+        """Rectangles (i0, i1, j0, j1) of at most sub x sub control points tiling each patch."""
+        for P in patches:
+            su = max(1, int(np.ceil(P.n_u / sub))); sv = max(1, int(np.ceil(P.n_v / sub)))
+            eu = np.round(np.linspace(0, P.n_u, su + 1)).astype(int); ev = np.round(np.linspace(0, P.n_v, sv + 1)).astype(int)
+            for b in range(sv):
+                for a in range(su):
+                    yield P, (eu[a], eu[a + 1], ev[b], ev[b + 1])
 
     def _finish_block(self, nodes, G, n_s, dof, ncp, cpo, n_own):
         """Envelope (variable panel heights) and dof maps of one ordered block."""
@@ -133,10 +149,13 @@ class SchwarzSetup:
         inv_sz = nbr.astype(np.int64) * NB * NB
         off_inv = np.concatenate([[0], np.cumsum(inv_sz)[:-1]]).astype(np.int64)
         glob = np.concatenate([b["glob"] for b in self.blocks])
-        loc = np.full((nb, S.N), -1, dtype=np.int32)
-        for i, b in enumerate(self.blocks):
-            g = b["glob"]; m = g >= 0
-            loc[i, g[m]] = np.nonzero(m)[0]
+        # global -> local lookup of each block: sorted global dofs + their local index
+        gs, ls, off_g = [], [], [0]
+        for b in self.blocks:
+            g = b["glob"]; m = np.nonzero(g >= 0)[0]
+            o = np.argsort(g[m], kind="stable")
+            gs.append(g[m][o]); ls.append(m[o].astype(np.int32)); off_g.append(off_g[-1] + len(m))
+        gs = np.concatenate(gs).astype(np.int32); ls = np.concatenate(ls); off_g = np.asarray(off_g, dtype=np.int64)
         # prolongation gather: dof d <- every block-local copy, in block order
         src = np.nonzero(glob >= 0)[0]
         d = glob[src]
@@ -146,6 +165,6 @@ class SchwarzSetup:
         np.cumsum(np.bincount(d, minlength=S.N), out=zptr[1:])
         return dict(nblocks=nb, n_pad=n_pad, nbr=nbr, off_j=off_j, mbj=mbj, rlen=rlen, off_col=off_col,
                     step_mb=step_mb, off_y=off_y, off_inv=off_inv,
-                    glob=glob.astype(np.int32), loc=loc, zptr=zptr, zsrc=zsrc, n_y=int(n_pad.sum()),
+                    glob=glob.astype(np.int32), gs=gs, ls=ls, off_g=off_g, zptr=zptr, zsrc=zsrc, n_y=int(n_pad.sum()),
                     band_len=band_len, inv_len=int(inv_sz.sum()),
                     max_nbr=int(nbr.max()), max_mb=int(mbj.max()), max_n_pad=int(n_pad.max()))

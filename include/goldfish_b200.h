@@ -193,12 +193,15 @@ typedef struct GfSchwarz {
   const int64_t* off_y;           /* [nblocks] offsets into y / glob                  */
   const int64_t* off_inv;         /* [nblocks] offsets into invd                      */
   const int32_t* glob;            /* [n_y] local -> global dof, -1 = padding          */
-  const int32_t* loc;             /* [nblocks][N] global -> local dof, -1 = absent    */
+  const int32_t* gs;              /* per block: sorted global dofs ...                */
+  const int32_t* ls;              /* ... and their local index (global -> local lookup) */
+  const int64_t* off_g;           /* [nblocks+1] offsets into gs / ls                 */
   const int64_t* zptr;            /* [N+1] prolongation gather                        */
   const int64_t* zsrc;            /* [..] indices into y                              */
   double* band;                   /* factor storage: nb x nb blocks                   */
   double* invd;                   /* inverses of the diagonal factor blocks           */
   double* y;                      /* [n_y] block-local vectors                        */
+  double* s;                      /* [n_y] backward-sweep accumulators                */
   uint32_t* barrier;              /* [nblocks] group barrier counters                 */
   int32_t* flag;                  /* device flag: non-SPD block met                   */
 } GfSchwarz;
