@@ -116,16 +116,25 @@ class Step:
         self.gT = torch.zeros(S.n_th, dtype=torch.float64, device=dm.device)
         self.info = {}
 
-    def __call__(self):
+    def __call__(self, timers=None):
         import ctypes as C
         from goldfish_b200 import _capi as capi
         dm, S = self.dm, self.dm.sym
+        torch = self.torch
+
+        def mark(name):
+            if timers is not None:
+                e = torch.cuda.Event(enable_timing=True); e.record(); timers.append((name, e))
+        mark("start")
         dm.newton(max_it=30, rtol=1e-3)
+        mark("newton (assemble R,K + factor + PCG per iteration)")
         kits = list(dm.newton_krylov_its)
         dm.assemble(tangent=True, functionals=True, shape=True, thickness=True)
+        mark("linearize (K, W, V, dR/dCP x3, dR/dt, dW/d*)")
         self.rhs.copy_(dm.dWdu)
         capi.check(dm.lib.gf_mask_vec(C.byref(dm.model), C.c_void_p(self.rhs.data_ptr()), dm._stream()), "mask")
         dm.solve(self.rhs, self.lam)
+        mark("adjoint solve")
         kits.append(dm.last_krylov_its)
         for i in range(len(S.opt_field)):
             self.gP[i].copy_(dm.dWdP[i][:S.P_ncols[i]])
@@ -134,6 +143,7 @@ class Step:
                 dm.spmv(dm.penP[i][0], self.lam, self.gP[i], alpha=-1.0, beta=1.0, transpose=True)
         self.gT.copy_(dm.dWdt[:S.n_th])
         dm.spmv(dm.T, self.lam, self.gT, alpha=-1.0, beta=1.0, transpose=True)
+        mark("gradient products (dR/dp)^T lam")
         self.info = {"newton_its": len(dm.newton_history) - 1, "krylov_its": kits}
 
 
@@ -305,7 +315,11 @@ def main():
     asm_ms = time_kernel(torch, lambda: dm.assemble(tangent=True, residual=True), 5, flush)
     nq = S.nq
     asm_flops = S.num_elements * nq * 29376.0
-    kernels = {"spmv_ms": spmv_ms, "spmv_gbs": achieved,
+    timers = []
+    step(timers); torch.cuda.synchronize()
+    phases = {timers[i][0]: round(timers[i - 1][1].elapsed_time(timers[i][1]), 2) for i in range(1, len(timers))}
+    fac_ms = time_kernel(torch, lambda: dm.factor_preconditioner(), 2, flush)
+    kernels = {"phase_ms": phases, "precond_factor_ms": fac_ms, "spmv_ms": spmv_ms, "spmv_gbs": achieved,
                "assemble_RK_ms": asm_ms, "assemble_RK_material_tflops": asm_flops / (asm_ms * 1e-3) / 1e12,
                "assemble_RK_gbs_algorithmic": (8 * dm.K.nnz + 8 * (4 * S.n_scalar + S.N + S.n_th)) / (asm_ms * 1e-3) / 1e9,
                "newton_its": step.info.get("newton_its"), "krylov_its": step.info.get("krylov_its")}

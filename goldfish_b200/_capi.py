@@ -103,6 +103,7 @@ SIGNATURES = {
                C.POINTER(C.c_int), C.POINTER(c_f64), c_vp],
     "gf_schwarz_factor": [C.POINTER(GfSchwarz), C.POINTER(GfCsr), c_vp],
     "gf_schwarz_apply": [C.POINTER(GfSchwarz), c_vp, c_vp, c_i64, c_vp],
+    "gf_schwarz_apply2": [C.POINTER(GfSchwarz), c_vp, c_vp, c_i64, C.POINTER(GfSchwarz), c_vp, c_vp, c_i64, c_vp],
     "gf_dot_slot0": [c_i64, c_vp, c_vp, c_vp, C.c_int, c_vp],
     "gf_precond_apply": [C.POINTER(GfPrecond), c_vp, c_vp, c_i64, c_vp],
     "gf_jacobi_setup": [C.POINTER(GfCsr), c_vp, c_vp],

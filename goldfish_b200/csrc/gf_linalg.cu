@@ -285,17 +285,17 @@ __global__ void k_zero_list(const int32_t* list, int64_t n, double* v) {
 
 extern "C" int gf_precond_apply(const GfPrecond* pc, const double* r, double* z, int64_t n, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = gf_schwarz_apply(pc->fine, r, z, n, st);
-  if (rc || !pc->coarse) return rc;
-  rc = gf_spmv(&pc->Rt, r, pc->rc, 1.0, 0.0, st);
+  if (!pc->coarse) return gf_schwarz_apply(pc->fine, r, z, n, st);
+  int rc = gf_spmv(&pc->Rt, r, pc->rc, 1.0, 0.0, st);       // restriction r_c = P^T r
   if (rc) return rc;
   if (pc->n_bc_c > 0) {
     k_zero_list<<<vec_grid(pc->n_bc_c), RED_THREADS, 0, st>>>(pc->bc_c, pc->n_bc_c, pc->rc);
     count_launch(1);
   }
-  rc = gf_schwarz_apply(pc->coarse, pc->rc, pc->zc, pc->Rt.nrows, st);
+  // fine block solves and the coarse solve share one cooperative launch
+  rc = gf_schwarz_apply2(pc->fine, r, z, n, pc->coarse, pc->rc, pc->zc, pc->Rt.nrows, st);
   if (rc) return rc;
-  return gf_spmv(&pc->P, pc->zc, z, 1.0, 1.0, st);
+  return gf_spmv(&pc->P, pc->zc, z, 1.0, 1.0, st);            // z += P z_c
 }
 
 extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, const GfPrecond* pre,

@@ -17,6 +17,7 @@
 //            columns with a per-group global-memory barrier per step
 //   z = sum_i R_i^T (L_i L_i^T)^-1 R_i r  assembled by a fixed-order gather.
 #include "gf_common.cuh"
+#include <stdlib.h>
 
 namespace gf {
 
@@ -203,10 +204,13 @@ __global__ void k_sw_gather_out(GfSchwarz S, double* __restrict__ z, int64_t n) 
 __device__ __forceinline__ void group_barrier(unsigned* cnt, unsigned target) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(cnt, 1u);
-    while (*((volatile unsigned*)cnt) < target) {}
-    __threadfence();
+    // release-increment / acquire-spin at gpu scope (bar.sync makes the CTA's stores
+    // happen-before the release; cumulativity publishes them to the other CTAs)
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+    } while (v < target);
   }
   __syncthreads();
 }
@@ -284,9 +288,15 @@ __device__ __forceinline__ void load_blk(const double* __restrict__ L, int w, in
   for (int rr = 0; rr < 8; ++rr) { Lr[2 * rr] = __ldcs(p + rr * NB + lane); Lr[2 * rr + 1] = __ldcs(p + rr * NB + lane + 32); }
 }
 
+// Fine patch blocks and (optionally) the single coarse block run in ONE cooperative
+// launch: CTAs [0, nf*G) serve fine blocks first_block.., CTAs beyond serve the coarse block.
 __global__ void __launch_bounds__(256)
-k_sw_solve(GfSchwarz S, int G, int first_block) {
-  const int i = first_block + blockIdx.x / G, cta = blockIdx.x % G;
+k_sw_solve(GfSchwarz Sf, int G_f, int first_block, int nf, GfSchwarz Sc, int G_c) {
+  const bool is_c = (int)blockIdx.x >= nf * G_f;
+  const GfSchwarz& S = is_c ? Sc : Sf;
+  const int G = is_c ? G_c : G_f;
+  const int bx = is_c ? (int)blockIdx.x - nf * G_f : (int)blockIdx.x;
+  const int i = is_c ? 0 : first_block + bx / G, cta = bx % G;
   __shared__ double xs[NB];
   __shared__ double red[8][NB];
   const int nbr = S.nbr[i];
@@ -430,40 +440,67 @@ extern "C" int gf_schwarz_factor(const GfSchwarz* S, const GfCsr* K, void* strea
   return check_launch("gf_schwarz_factor");
 }
 
-extern "C" int gf_schwarz_apply(const GfSchwarz* S, const double* r, double* z, int64_t n, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  int g = (int)((S->n_y + 255) / 256); if (g > 2048) g = 2048;
-  k_sw_gather_in<<<g, 256, 0, st>>>(*S, r);
-  cudaError_t e = cudaMemsetAsync(S->barrier, 0, sizeof(unsigned) * S->nblocks, st);
-  if (e != cudaSuccess) return set_cuda_error(e, "gf_schwarz_apply memset");
-  GfSchwarz Sv = *S;
+static int sw_caps(int* sms_out, int* occ_out) {
   static int sms = 0, occ = 0;
   if (!sms) {
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sw_solve, 256, 0);
-    if (occ > 2) occ = 2;
+    int lim = 4;
+    if (const char* ev = getenv("GF_SW_OCC")) lim = atoi(ev);
+    if (occ > lim) occ = lim;
     if (occ < 1) occ = 1;
   }
-  const int cap = sms * occ;                   // all CTAs of one launch must be co-resident
-  int G = cap / S->nblocks;
-  if (G > S->max_mb) G = S->max_mb;            // one panel block per CTA and step is enough
-  if (S->ctas_per_block > 0 && G > S->ctas_per_block) G = S->ctas_per_block;
+  *sms_out = sms; *occ_out = occ;
+  return sms * occ;
+}
+
+// z_f = sum_i R_i^T A_i^-1 R_i r_f  (fine blocks of Sf)  and, if Sc != NULL, z_c = Kc^-1 r_c
+// (single block of Sc) with both sets of triangular sweeps running concurrently.
+extern "C" int gf_schwarz_apply2(const GfSchwarz* Sf, const double* r_f, double* z_f, int64_t n_f,
+                                 const GfSchwarz* Sc, const double* r_c, double* z_c, int64_t n_c, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int g = (int)((Sf->n_y + 255) / 256); if (g > 2048) g = 2048;
+  k_sw_gather_in<<<g, 256, 0, st>>>(*Sf, r_f);
+  cudaError_t e = cudaMemsetAsync(Sf->barrier, 0, sizeof(unsigned) * Sf->nblocks, st);
+  if (Sc) {
+    int gc = (int)((Sc->n_y + 255) / 256); if (gc > 2048) gc = 2048;
+    k_sw_gather_in<<<gc, 256, 0, st>>>(*Sc, r_c);
+    if (e == cudaSuccess) e = cudaMemsetAsync(Sc->barrier, 0, sizeof(unsigned) * Sc->nblocks, st);
+    count_launch(1);
+  }
+  if (e != cudaSuccess) return set_cuda_error(e, "gf_schwarz_apply memset");
+  int sms, occ;
+  const int cap = sw_caps(&sms, &occ);           // all CTAs of one launch must be co-resident
+  GfSchwarz Sfv = *Sf, Scv = Sc ? *Sc : *Sf;
+  int G_c = 0;
+  if (Sc) { G_c = cap / 6; if (G_c > Sc->max_mb) G_c = Sc->max_mb; if (G_c < 1) G_c = 1; }
+  int G = (cap - G_c) / Sf->nblocks;
+  if (G > Sf->max_mb) G = Sf->max_mb;            // one panel block per CTA and step is enough
   if (G < 1) G = 1;
-  const int per_launch = cap / G;              // patch blocks per cooperative launch
-  for (int b0 = 0; b0 < S->nblocks; b0 += per_launch) {
-    int nb_l = S->nblocks - b0; if (nb_l > per_launch) nb_l = per_launch;
+  const int per_launch = (cap - G_c) / G;        // fine blocks per cooperative launch
+  for (int b0 = 0; b0 < Sf->nblocks; b0 += per_launch) {
+    int nb_l = Sf->nblocks - b0; if (nb_l > per_launch) nb_l = per_launch;
     int first = b0;
-    void* args[] = {&Sv, &G, &first};
-    e = cudaLaunchCooperativeKernel((void*)k_sw_solve, dim3(nb_l * G), dim3(256), args, 0, st);
+    int gcl = (b0 == 0) ? G_c : 0;               // the coarse block rides along with the first batch
+    void* args[] = {&Sfv, &G, &first, &nb_l, &Scv, &gcl};
+    e = cudaLaunchCooperativeKernel((void*)k_sw_solve, dim3(nb_l * G + gcl), dim3(256), args, 0, st);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchCooperativeKernel(k_sw_solve)");
     count_launch(1);
   }
-  count_launch(-1);
-  int g2 = (int)((n + 255) / 256); if (g2 > 2048) g2 = 2048;
-  k_sw_gather_out<<<g2, 256, 0, st>>>(*S, z, n);
-  count_launch(2);
+  int g2 = (int)((n_f + 255) / 256); if (g2 > 2048) g2 = 2048;
+  k_sw_gather_out<<<g2, 256, 0, st>>>(*Sf, z_f, n_f);
+  if (Sc) {
+    int g3 = (int)((n_c + 255) / 256); if (g3 > 2048) g3 = 2048;
+    k_sw_gather_out<<<g3, 256, 0, st>>>(*Sc, z_c, n_c);
+    count_launch(1);
+  }
+  count_launch(1);
   return check_launch("gf_schwarz_apply");
+}
+
+extern "C" int gf_schwarz_apply(const GfSchwarz* S, const double* r, double* z, int64_t n, void* stream) {
+  return gf_schwarz_apply2(S, r, z, n, nullptr, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int gf_dot_slot0(int64_t n, const double* x, const double* y, double* partial2, int grid, void* stream) {

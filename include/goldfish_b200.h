@@ -207,6 +207,9 @@ typedef struct GfSchwarz {
 } GfSchwarz;
 int gf_schwarz_factor(const GfSchwarz* s, const GfCsr* K, void* stream);
 int gf_schwarz_apply(const GfSchwarz* s, const double* r, double* z, int64_t n, void* stream);
+/* fine blocks + one coarse block, triangular sweeps of both in one cooperative launch */
+int gf_schwarz_apply2(const GfSchwarz* fine, const double* r_f, double* z_f, int64_t n_f,
+                      const GfSchwarz* coarse, const double* r_c, double* z_c, int64_t n_c, void* stream);
 int gf_dot_slot0(int64_t n, const double* x, const double* y, double* partial2, int grid, void* stream);
 
 /* Two-level preconditioner  z = sum_i R_i^T A_i^-1 R_i r  +  P Kc^-1 P^T r :

@@ -31,7 +31,7 @@ if __name__ == "__main__":
     run("slr4", problems.scordelis_lo(num_el=4))
     run("plate", problems.plate(os.path.join(os.path.dirname(__file__), "..", "tests/golden/plate_c1_input.npz")))
     for ne in sizes:
-        for sub, nc in ((1000, 16), (64, 16), (48, 16), (32, 16), (32, 24), (24, 24)):
+        for sub, nc in ((64, 16), (64, 24)):
             t0 = time.time(); pr = problems.cylinder(n_el=ne)
             dm = run("cyl%d sub%d" % (ne, sub), pr, oracle=(ne <= 8), coarse_nc=nc, schwarz_sub=sub)
             torch.cuda.synchronize(); t1 = time.time(); dm.factor_preconditioner(); torch.cuda.synchronize()
