@@ -138,11 +138,11 @@ class Step:
         kits.append(dm.last_krylov_its)
         for i in range(len(S.opt_field)):
             self.gP[i].copy_(dm.dWdP[i][:S.P_ncols[i]])
-            dm.spmv(dm.P[i], self.lam, self.gP[i], alpha=-1.0, beta=1.0, transpose=True)
+            dm.spmv_global(dm.P[i], self.lam, self.gP[i], alpha=-1.0, beta=1.0, transpose=True)
             if dm.penP[i] is not None:
-                dm.spmv(dm.penP[i][0], self.lam, self.gP[i], alpha=-1.0, beta=1.0, transpose=True)
+                dm.spmv_global(dm.penP[i][0], self.lam, self.gP[i], alpha=-1.0, beta=1.0, transpose=True)
         self.gT.copy_(dm.dWdt[:S.n_th])
-        dm.spmv(dm.T, self.lam, self.gT, alpha=-1.0, beta=1.0, transpose=True)
+        dm.spmv_global(dm.T, self.lam, self.gT, alpha=-1.0, beta=1.0, transpose=True)
         mark("gradient products (dR/dp)^T lam")
         self.info = {"newton_its": len(dm.newton_history) - 1, "krylov_its": kits}
 
@@ -281,7 +281,7 @@ def main():
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
-    value = world * args.steps / (ms * 1e-3)      # N>1 currently runs N independent replicas
+    value = args.steps / (ms * 1e-3)              # one patch-sharded problem over all ranks (strong scaling)
 
     # ---- e2e through the facade, host arrays ----
     nm, ops = build_facade(pr, kw)
@@ -327,14 +327,14 @@ def main():
     if rank == 0:
         line = {"metric": "analysis+adjoint iters/s", "value": value, "unit": "iters/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "cylinder_4x2_ne%d: 8 non-matching bicubic NURBS patches, 10 intersections, "
                                        "shape fields 0,1,2 + per-patch thickness" % args.n_el,
                            "dofs": int(S.N), "elements": int(S.num_elements), "nnz_K": int(dm.K.nnz), "quad_pts_per_element": int(nq),
                            "cache": "512 MB flush buffer written between timed kernel launches; step working set > L2 at n_el >= 64",
-                           "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world},
-                "e2e": {"value": world * args.steps / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                           "parallelism": "1 GPU" if world == 1 else "patch-sharded over %d GPUs (rows + Schwarz blocks owned, vectors replicated, NCCL all-reduce)" % world},
+                "e2e": {"value": args.steps / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "k_spmv", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": None,

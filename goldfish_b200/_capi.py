@@ -78,9 +78,16 @@ class GfSchwarz(C.Structure):
                 ("band", c_vp), ("invd", c_vp), ("y", c_vp), ("s", c_vp), ("barrier", c_vp), ("flag", c_vp)]
 
 
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_int, c_vp)
+
+
+class GfDist(C.Structure):
+    _fields_ = [("n_ranges", c_i32), ("pad_", c_i32), ("ranges_h", c_vp), ("allreduce", ALLREDUCE_FN), ("ctx", c_vp)]
+
+
 class GfPrecond(C.Structure):
     _fields_ = [("fine", C.POINTER(GfSchwarz)), ("coarse", C.POINTER(GfSchwarz)), ("P", GfCsr), ("Rt", GfCsr),
-                ("rc", c_vp), ("zc", c_vp), ("bc_c", c_vp), ("n_bc_c", c_i64)]
+                ("rc", c_vp), ("zc", c_vp), ("bc_c", c_vp), ("n_bc_c", c_i64), ("dist", C.POINTER(GfDist))]
 
 
 class GfPcgWork(C.Structure):
@@ -99,7 +106,7 @@ SIGNATURES = {
     "gf_mask_vec": [C.POINTER(GfModel), c_vp, c_vp],
     "gf_spmv": [C.POINTER(GfCsr), c_vp, c_vp, c_f64, c_f64, c_vp],
     "gf_spmv_t": [C.POINTER(GfCsr), C.POINTER(GfCsrT), c_vp, c_vp, c_f64, c_f64, c_vp],
-    "gf_pcg": [C.POINTER(GfCsr), c_vp, c_vp, C.POINTER(GfPcgWork), C.POINTER(GfPrecond), c_f64, c_f64, C.c_int, C.c_int,
+    "gf_pcg": [C.POINTER(GfCsr), c_vp, c_vp, C.POINTER(GfPcgWork), C.POINTER(GfPrecond), C.POINTER(GfDist), c_f64, c_f64, C.c_int, C.c_int,
                C.POINTER(C.c_int), C.POINTER(c_f64), c_vp],
     "gf_schwarz_factor": [C.POINTER(GfSchwarz), C.POINTER(GfCsr), c_vp],
     "gf_schwarz_apply": [C.POINTER(GfSchwarz), c_vp, c_vp, c_i64, c_vp],

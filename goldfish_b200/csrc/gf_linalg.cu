@@ -285,7 +285,12 @@ __global__ void k_zero_list(const int32_t* list, int64_t n, double* v) {
 
 extern "C" int gf_precond_apply(const GfPrecond* pc, const double* r, double* z, int64_t n, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (!pc->coarse) return gf_schwarz_apply(pc->fine, r, z, n, st);
+  if (!pc->coarse) {
+    int rc0 = gf_schwarz_apply(pc->fine, r, z, n, st);
+    if (rc0 == 0 && pc->dist && pc->dist->n_ranges > 0 && pc->dist->allreduce(1, pc->dist->ctx))
+      return set_error(GF_ERR_CUDA, "all-reduce of the preconditioned residual failed");
+    return rc0;
+  }
   int rc = gf_spmv(&pc->Rt, r, pc->rc, 1.0, 0.0, st);       // restriction r_c = P^T r
   if (rc) return rc;
   if (pc->n_bc_c > 0) {
@@ -295,12 +300,17 @@ extern "C" int gf_precond_apply(const GfPrecond* pc, const double* r, double* z,
   // fine block solves and the coarse solve share one cooperative launch
   rc = gf_schwarz_apply2(pc->fine, r, z, n, pc->coarse, pc->rc, pc->zc, pc->Rt.nrows, st);
   if (rc) return rc;
-  return gf_spmv(&pc->P, pc->zc, z, 1.0, 1.0, st);            // z += P z_c
+  if (pc->dist && pc->dist->n_ranges > 0) {                   // sum the ranks' block contributions
+    rc = pc->dist->allreduce(1, pc->dist->ctx);
+    if (rc) return set_error(GF_ERR_CUDA, "all-reduce of the preconditioned residual failed");
+  }
+  return gf_spmv(&pc->P, pc->zc, z, 1.0, 1.0, st);            // z += P z_c (coarse level is replicated)
 }
 
 extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, const GfPrecond* pre,
-                      double rtol, double atol, int max_it, int check_every, int* iters, double* relres,
-                      void* stream) {
+                      const GfDist* dist, double rtol, double atol, int max_it, int check_every, int* iters,
+                      double* relres, void* stream) {
+  const bool sharded = dist && dist->n_ranges > 0;
   if (!A || !b || !x || !w) return set_error(GF_ERR_BADARG, "gf_pcg: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = A->nrows;
@@ -333,8 +343,26 @@ extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWor
   int rc = GF_ERR_NOCONV;
   while (it < max_it) {
     const int parity = it & 1;
-    k_spmv<<<gs, 256, 0, st>>>(*A, w->p, w->Ap, 1.0, 0.0, w->p, part1);
-    k_pcg_update<<<gv, RED_THREADS, 0, st>>>(n, w->p, w->Ap, w->dinv, x, w->r, w->z, part1, gs, w->scal,
+    int npart1 = gs;
+    if (!sharded) {
+      k_spmv<<<gs, 256, 0, st>>>(*A, w->p, w->Ap, 1.0, 0.0, w->p, part1);
+    } else {
+      // owned rows only, then sum over ranks; every rank then holds the full A p and
+      // computes the (identical) dot products itself -> no scalar all-reduce
+      e = cudaMemsetAsync(w->Ap, 0, (size_t)n * sizeof(double), st);
+      if (e != cudaSuccess) return set_cuda_error(e, "gf_pcg memset");
+      for (int q = 0; q < dist->n_ranges; ++q) {
+        const int64_t b0 = dist->ranges_h[2 * q], b1 = dist->ranges_h[2 * q + 1];
+        if (b1 <= b0) continue;
+        GfCsr sub = *A; sub.indptr = A->indptr + b0; sub.nrows = b1 - b0;
+        k_spmv<<<spmv_grid(sub.nrows), 256, 0, st>>>(sub, w->p, w->Ap + b0, 1.0, 0.0, nullptr, nullptr);
+        count_launch(1);
+      }
+      if (dist->allreduce(0, dist->ctx)) return set_error(GF_ERR_CUDA, "all-reduce of A p failed");
+      k_dot_partial<<<gv, RED_THREADS, 0, st>>>(n, w->p, w->Ap, part1);
+      npart1 = gv;
+    }
+    k_pcg_update<<<gv, RED_THREADS, 0, st>>>(n, w->p, w->Ap, w->dinv, x, w->r, w->z, part1, npart1, w->scal,
                                              parity, part2);
     if (pre) {
       int rc1 = gf_precond_apply(pre, w->r, w->z, n, st);

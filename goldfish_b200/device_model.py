@@ -69,7 +69,7 @@ class DeviceCsr:
 
 class DeviceModel:
     def __init__(self, problem, opt_field=(), shopt_surf_inds=(), device=None, symbolic=None,
-                 precond="schwarz", schwarz_layers=2, coarse_nc="auto", schwarz_sub=64):
+                 precond="schwarz", schwarz_layers=2, coarse_nc="auto", schwarz_sub=64, distributed=None):
         if not torch.cuda.is_available():
             raise capi.GoldfishError("goldfish_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = capi.load()
@@ -78,6 +78,19 @@ class DeviceModel:
         S = self.sym
         dv = self.device
         self._keep = []
+        # ---- patch-sharded multi-GPU mode (one process per GPU, torch.distributed / NCCL) ----
+        import torch.distributed as tdist
+        if distributed is None:
+            distributed = tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1
+        self.dist = tdist if distributed else None
+        self.rank = tdist.get_rank() if distributed else 0
+        self.world = tdist.get_world_size() if distributed else 1
+        from .partition import lpt_partition, shard_symbolic
+        self.owner = lpt_partition([P.nel for P in S.patches], self.world)
+        self.own_patches = [P.index for P in S.patches if self.owner[P.index] == self.rank]
+        self._shard = shard_symbolic(S, self.owner, self.rank)
+        self.own_ranges = self._shard["own_ranges"]
+        self._color_elem, self._color_ptr = self._shard["color_elem"], self._shard["color_ptr"]
 
         def up(a, dtype=None):
             a = np.ascontiguousarray(a if dtype is None else np.asarray(a).astype(dtype))
@@ -102,17 +115,23 @@ class DeviceModel:
         self.t_patches = up(raw)
         self.t = {}
         for k, a, dt in (("elem_patch", S.elem_patch, np.int32), ("elem_eu", S.elem_eu, np.int32),
-                         ("elem_ev", S.elem_ev, np.int32), ("color_elem", S.color_elem, np.int32),
+                         ("elem_ev", S.elem_ev, np.int32), ("color_elem", self._color_elem if len(self._color_elem) else np.zeros(1, np.int32), np.int32),
                          ("tab_u", S.tab_u, np.float64), ("tab_v", S.tab_v, np.float64),
                          ("first_cp_u", S.first_cp_u, np.int32), ("first_cp_v", S.first_cp_v, np.int32),
                          ("span_h_u", S.span_h_u, np.float64), ("span_h_v", S.span_h_v, np.float64),
                          ("qw", S.qw, np.float64), ("tw_lin", S.tw_lin, np.float64),
                          ("bc", S.bc_mask, np.uint8), ("bc_list", S.bc_list, np.int32),
-                         ("row_nlow", S.row_nlow, np.int32), ("f_const", S.f_const, np.float64)):
+                         ("row_nlow", S.row_nlow, np.int32),
+                         ("f_const", S.f_const if self.rank == 0 else np.zeros_like(S.f_const), np.float64)):
             self.t[k] = up(a, dt)
         for k, a in S.dirs.items():
             self.t[k] = up(a, np.int32)
-        self.color_ptr_h = np.ascontiguousarray(S.color_ptr, dtype=np.int32)
+        self.color_ptr_h = np.ascontiguousarray(self._color_ptr, dtype=np.int32)
+        own_rows = np.zeros(S.N, dtype=bool)
+        for b0, b1 in self.own_ranges:
+            own_rows[b0:b1] = True
+        self.t["bc_list_own"] = up(S.bc_list[own_rows[S.bc_list]] if len(S.bc_list) else np.zeros(0, np.int32), np.int32)
+        self.n_bc_own = int(own_rows[S.bc_list].sum()) if len(S.bc_list) else 0
         # state
         self.cp = up(S.cp0, np.float64)
         self.u = torch.zeros(S.N, dtype=torch.float64, device=dv)
@@ -185,10 +204,11 @@ class DeviceModel:
         self.pen_t = {}
         q = capi.GfPenalty()
         q.n_eval = pen["n_eval"]
+        pen = self._shard["pen"]          # destinations restricted to owned rows (all of them on 1 GPU)
         if pen["n_eval"] > 0:
             for k in ("connA", "connB", "connC0", "connC1", "basA", "basB", "basC0", "basC1", "tpar", "alpha",
                       "dofA", "dofB", "R_ptr", "R_item", "R_row", "K_ptr", "K_item", "K_pos"):
-                self.pen_t[k] = up(pen[k])
+                self.pen_t[k] = up(pen[k] if len(pen[k]) else np.zeros(1, pen[k].dtype))
                 setattr(q, k, _ptr(self.pen_t[k]))
             ne = pen["n_eval"]
             self.pen_g = torch.zeros(ne * 18, dtype=torch.float64, device=self.device)
@@ -196,14 +216,14 @@ class DeviceModel:
             self.pen_HuX = torch.zeros(ne * 324, dtype=torch.float64, device=self.device)
             q.g, q.Huu, q.HuX = _ptr(self.pen_g), _ptr(self.pen_Huu), _ptr(self.pen_HuX)
             q.nR, q.nK = pen["nR"], pen["nK"]
-            for pp in S.penP:
-                if pp["n_dest"] == 0:
+            for pp in self._shard["penP"]:
+                if pp.get("n_dest", 0) == 0:
                     self.penP.append(None)
                     continue
                 M = DeviceCsr(S.N, S.P_ncols[S.opt_field.index(pp["field"])], pp["indptr"], pp["indices"], self.device)
                 s = capi.GfPenaltyP()
                 s.n_dest = pp["n_dest"]
-                arrs = [up(pp[k]) for k in ("ptr", "item_eval", "item_code", "pos")]
+                arrs = [up(pp[k] if len(pp[k]) else np.zeros(1, pp[k].dtype)) for k in ("ptr", "item_eval", "item_code", "pos")]
                 s.ptr, s.item_eval, s.item_code, s.pos = [_ptr(a) for a in arrs]
                 s.vals = _ptr(M.vals)
                 s.field = pp["field"]
@@ -231,6 +251,9 @@ class DeviceModel:
                 m.P[f] = self.P[S.opt_field.index(f)].c_struct()
         m.T = self.T.c_struct()
         self.model = m
+        m2 = capi.GfModel.from_buffer_copy(m)      # same model, zero-dof list restricted to owned rows
+        m2.bc_list, m2.n_bc = _ptr(self.t["bc_list_own"]), self.n_bc_own
+        self.model_own_bc = m2
         o = capi.GfShellOut()
         o.R, o.WV, o.dWdu = _ptr(self.R), _ptr(self.WV), _ptr(self.dWdu)
         for f in range(3):
@@ -315,11 +338,35 @@ class DeviceModel:
                         pp[0].vals.zero_()
                         capi.check(lib.gf_penalty_gather_P(C.byref(self.pen_struct), C.byref(pp[1]), st), "gather_P")
         if residual:
+            self.allreduce(self.R)
             capi.check(lib.gf_mask_vec(C.byref(self.model), _ptr(self.R), st), "gf_mask_vec")
         if tangent:
-            capi.check(lib.gf_bc_set_diag(C.byref(self.model), 1.0, st), "gf_bc_set_diag")
+            capi.check(lib.gf_bc_set_diag(C.byref(self.model_own_bc), 1.0, st), "gf_bc_set_diag")
+            self._K_full = self.dist is None
         if functionals:
             capi.check(lib.gf_reduce_wv(S.num_elements, _ptr(self.WV), _ptr(self.wv_sum), st), "gf_reduce_wv")
+            self.allreduce(self.wv_sum)
+        if self.dist is not None:
+            if shape and S.opt_field:
+                for a in self.dWdP + self.dVdP:
+                    self.allreduce(a)
+            if thickness:
+                for a in (self.dWdt, self.dVdt, self.dWdu):
+                    self.allreduce(a)
+
+    def allreduce(self, t):
+        """Sum a device tensor over the ranks (no-op in single-GPU runs)."""
+        if self.dist is not None:
+            self.dist.all_reduce(t)
+        return t
+
+    def replicate_K(self):
+        """Distributed runs keep only the owned rows of K after assembly; the
+        preconditioner set-up needs the rows of the overlap nodes too, so the
+        values are summed over the ranks once per factorisation (NVLink all-reduce)."""
+        if self.dist is not None and not getattr(self, "_K_full", False):
+            self.dist.all_reduce(self.K.vals)
+            self._K_full = True
 
     # ------------------------------------------------------------ linear algebra
     def spmv(self, A, x, y, alpha=1.0, beta=0.0, transpose=False):
@@ -330,6 +377,24 @@ class DeviceModel:
         else:
             capi.check(self.lib.gf_spmv(C.byref(cs), _ptr(x), _ptr(y), alpha, beta, st), "gf_spmv")
         return y
+
+    def spmv_global(self, A, x, y, alpha=1.0, beta=0.0, transpose=False):
+        """y = beta y + alpha A x (or A^T x) with x, y replicated on every rank."""
+        if self.dist is None:
+            return self.spmv(A, x, y, alpha, beta, transpose)
+        tmp = torch.zeros_like(y)
+        if A is self.K:
+            # K may or may not be replicated at this point: use the owned rows only (K symmetric)
+            cs = A.c_struct()
+            for b0, b1 in self.own_ranges:
+                sub = capi.GfCsr.from_buffer_copy(cs)
+                sub.indptr = C.c_void_p(A.indptr.data_ptr() + 8 * int(b0)); sub.nrows = int(b1 - b0)
+                capi.check(self.lib.gf_spmv(C.byref(sub), _ptr(x), C.c_void_p(tmp.data_ptr() + 8 * int(b0)), 1.0, 0.0,
+                                            self._stream()), "gf_spmv")
+        else:
+            self.spmv(A, x, tmp, 1.0, 0.0, transpose)      # rows of other ranks hold zeros
+        self.allreduce(tmp)
+        return self.axpby(alpha, tmp, beta, y)
 
     def axpby(self, a, x, b, y):
         capi.check(self.lib.gf_axpby(x.numel(), a, _ptr(x), b, _ptr(y), self._stream()), "gf_axpby")
@@ -345,12 +410,13 @@ class DeviceModel:
         if self._pc is None:
             pc = capi.GfPrecond()
             pc.fine = C.pointer(self._schwarz())
+            pc.dist = C.pointer(self._dist_struct())
             self._coarse = None
             if self.coarse_nc > 0:
                 from . import coarse as coarse_mod
                 cpr, P = coarse_mod.build(self.problem, nc=self.coarse_nc)
                 cpr["alpha_override"] = self.sym.itf_alpha
-                cm = DeviceModel(cpr, device=self.device, precond="schwarz", coarse_nc=0)
+                cm = DeviceModel(cpr, device=self.device, precond="schwarz", coarse_nc=0, distributed=False)
                 cm._single_block = True
                 Pd = DeviceCsr(P.shape[0], P.shape[1], P.indptr, P.indices, self.device)
                 Pd.vals.copy_(torch.from_numpy(P.data))
@@ -371,8 +437,11 @@ class DeviceModel:
         """Build (once) the overlapping-Schwarz block structure and its HBM storage."""
         if self._sw is None:
             from .schwarz import SchwarzSetup, NB
-            A = SchwarzSetup(self.sym, layers=self.schwarz_layers, sub=self.schwarz_sub,
-                             single_block=getattr(self, "_single_block", False)).arrays()
+            SW = SchwarzSetup(self.sym, layers=self.schwarz_layers, sub=self.schwarz_sub,
+                              single_block=getattr(self, "_single_block", False))
+            if self.dist is not None:
+                SW.keep_blocks([self.owner[b["patch"]] == self.rank for b in SW.blocks])
+            A = SW.arrays()
             dv = self.device
             t = {k: torch.from_numpy(np.ascontiguousarray(A[k])).to(dv)
                  for k in ("n_pad", "nbr", "off_j", "mbj", "rlen", "off_col", "off_y", "off_inv", "glob", "gs", "ls", "off_g", "zptr", "zsrc")}
@@ -395,9 +464,30 @@ class DeviceModel:
             self._sw = (s, t, step_mb, A)
         return self._sw[0]
 
+    def _dist_struct(self):
+        if getattr(self, "_dist_c", None) is None:
+            d = capi.GfDist()
+            if self.dist is not None:
+                self._ranges_h = np.ascontiguousarray(self.own_ranges if len(self.own_ranges) else np.zeros((1, 2), np.int64))
+                d.n_ranges = max(1, len(self.own_ranges))
+                d.ranges_h = self._ranges_h.ctypes.data_as(C.c_void_p)
+
+                def _ar(which, ctx):
+                    try:
+                        self.dist.all_reduce(self.w_Ap if which == 0 else self.w_z)
+                        return 0
+                    except Exception as e:  # surfaced as a GF error by the caller
+                        print("all-reduce failed:", e)
+                        return 1
+                self._ar_cb = capi.ALLREDUCE_FN(_ar)
+                d.allreduce = self._ar_cb
+            self._dist_c = d
+        return self._dist_c
+
     def factor_preconditioner(self):
         """(Re)build the preconditioner from the current K values."""
         st = self._stream()
+        self.replicate_K()
         cs = self.K.c_struct()
         if self.precond == "schwarz":
             pc = self._precond_struct()
@@ -422,7 +512,7 @@ class DeviceModel:
             self.factor_preconditioner()
         pre = C.byref(self._precond_struct()) if self.precond == "schwarz" else None
         its = C.c_int(0); rel = C.c_double(0.0)
-        rc = self.lib.gf_pcg(C.byref(cs), _ptr(b), _ptr(x), C.byref(self.pcg_work), pre,
+        rc = self.lib.gf_pcg(C.byref(cs), _ptr(b), _ptr(x), C.byref(self.pcg_work), pre, C.byref(self._dist_struct()),
                              self.krylov_rtol if rtol is None else rtol, 0.0,
                              self.krylov_max_it if max_it is None else max_it, self.krylov_check_every,
                              C.byref(its), C.byref(rel), st)

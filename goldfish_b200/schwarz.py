@@ -86,6 +86,11 @@ class SchwarzSetup:
             order = np.lexsort((kf, ks))
             nodes = nodes[order]
             self.blocks.append(self._finish_block(nodes, G, n_s, dof, ncp, cpo, n_own=len(own)))
+            self.blocks[-1]["patch"] = P.index
+
+    def keep_blocks(self, mask):
+        """Distributed runs: each rank factors and solves only the blocks of its own patches."""
+        self.blocks = [b for b, m in zip(self.blocks, mask) if m]
 
     @staticmethod
     def _subdomains(patches, sub):

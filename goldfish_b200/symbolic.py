@@ -401,6 +401,7 @@ class Symbolic:
         ps = self.scalar_patch[ud]
         pen["R_row"] = np.stack([dof[ps] + i * ncp[ps] + (ud - cpo[ps]) for i in range(3)], axis=1).astype(np.int32)
         pen["nR"] = len(ud)
+        pen["R_dest_patch"] = ps.astype(np.int32)
         # ---- K gather: destination = (row CP, col CP) ----
         r = np.repeat(nodes, 32, axis=1).ravel(); c = np.tile(nodes, (1, 32)).ravel()
         la = np.repeat(np.arange(32), 32); lb = np.tile(np.arange(32), 32)
@@ -421,6 +422,7 @@ class Symbolic:
                 pos[:, i, j] = np.where(rbc | cbc, -1, pos[:, i, j])
         pen["K_pos"] = np.ascontiguousarray(pos.reshape(-1, 9))
         pen["nK"] = len(uk)
+        pen["K_dest_patch"] = pr.astype(np.int32)
         # ---- dR/dCP_f penalty part ----
         self.penP = []
         for fi, field in enumerate(self.opt_field):
@@ -457,6 +459,7 @@ class Symbolic:
         out["ptr"] = np.append(start, len(key)).astype(np.int64)
         out["item_eval"] = ev[order].astype(np.int32); out["item_code"] = code[order].astype(np.int32)
         out["n_dest"] = len(uk)
+        out["dest_patch"] = self.scalar_patch[ur].astype(np.int32)
         # CSR of the penalty part: rows = dofs, cols = pcol + local cp
         pr, pc = self.scalar_patch[ur], self.scalar_patch[uc]
         col = pcol[pc] + (uc - cpo[pc])

@@ -100,7 +100,7 @@ class DeviceMat:
 
     def _apply(self, x, y, transpose):
         for i, A in enumerate(self.parts):
-            self.owner.spmv(A, x, y, 1.0, 0.0 if i == 0 else 1.0, transpose=transpose)
+            self.owner.spmv_global(A, x, y, 1.0, 0.0 if i == 0 else 1.0, transpose=transpose)
         return y
 
     def mult(self, x, y):

@@ -216,6 +216,19 @@ int gf_dot_slot0(int64_t n, const double* x, const double* y, double* partial2, 
  * `fine` = overlapping patch blocks, `coarse` = ONE block holding the factor of
  * the coarse-spline operator (same shells + coupling re-discretised on a coarser
  * knot vector by the same kernels), P = knot-insertion prolongation, Rt = P^T. */
+/* Patch-sharded multi-GPU runs (one process per GPU): vectors are replicated, matrix
+ * rows / Schwarz blocks are owned.  The library computes the owned part of A p and of
+ * the preconditioned residual and asks the host (torch.distributed over NCCL) to
+ * sum them across ranks:  which = 0 -> work->Ap, which = 1 -> work->z. */
+typedef int (*gf_allreduce_fn)(int which, void* ctx);
+typedef struct GfDist {
+  int32_t n_ranges;               /* 0 = single process                               */
+  int32_t pad_;
+  const int64_t* ranges_h;        /* HOST [n_ranges][2] owned row ranges [begin, end)  */
+  gf_allreduce_fn allreduce;
+  void* ctx;
+} GfDist;
+
 typedef struct GfPrecond {
   const GfSchwarz* fine;
   const GfSchwarz* coarse;        /* may be NULL: one-level                           */
@@ -223,6 +236,7 @@ typedef struct GfPrecond {
   double* rc; double* zc;         /* [Nc] work vectors                                */
   const int32_t* bc_c;            /* coarse zero-dofs                                 */
   int64_t n_bc_c;
+  const GfDist* dist;             /* NULL or n_ranges == 0: single process            */
 } GfPrecond;
 int gf_precond_apply(const GfPrecond* pc, const double* r, double* z, int64_t n, void* stream);
 
@@ -236,7 +250,8 @@ typedef struct GfPcgWork {
 /* Preconditioned CG on K x = b (K symmetric: nonmatching_opt.py:804-809).
  * Replaces solve_nonmatching_mat(..., 'direct') (utils/opt_utils.py:176,204). */
 int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, const GfPrecond* precond,
-           double rtol, double atol, int max_it, int check_every, int* iters, double* relres, void* stream);
+           const GfDist* dist, double rtol, double atol, int max_it, int check_every, int* iters,
+           double* relres, void* stream);
 int gf_jacobi_setup(const GfCsr* A, double* dinv, void* stream);
 
 /* small vector helpers on device */
