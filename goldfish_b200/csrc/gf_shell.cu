@@ -19,6 +19,7 @@
 // pattern (the M^T K M extraction of nonmatching_opt.py:688 is fused away:
 // we never leave the spline basis).
 #include "gf_common.cuh"
+#include <stdlib.h>
 
 namespace gf {
 
@@ -468,6 +469,255 @@ static int launch_mode(const GfModel* m, int what, const GfShellOut* out, cudaSt
   return check_launch("k_shell");
 }
 
+
+// ---------------------------------------------------------------------------------
+// Tangent pass, version 2: two quadrature points per warp pass.
+// Only the 15 g_u directions are needed for K, so lanes 0..15 serve point 2*it and
+// lanes 16..31 point 2*it+1 (lane & 15 = direction, lane 15 / 31 carry no seed).
+// The reference-configuration part of the point routine runs in plain doubles.
+// ---------------------------------------------------------------------------------
+struct WarpSmemK2 {
+  double Xc[16][4];
+  double uc[16][3];
+  double Phi[2][6][16];
+  double g[2][32];       // [gX 0..14 | t 15 | gu 16..30]
+  double Gv[2][16];      // grad values, [15] = J
+  double Ev[2];
+  double Hc[2][15][17];  // Hc[h][m][d] = d grad_m / d gu_d
+  double G[15][48];
+  double tw[2][16];
+  double the[16];
+  int ninfo[16][8];
+};
+
+__global__ void __launch_bounds__(128)
+k_shell_k2(GfModel M, GfShellOut O, int what, int color_begin, int color_count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpSmemK2& S = reinterpret_cast<WarpSmemK2*>(smem_raw)[warp];
+  const int slot = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (slot >= color_count) return;
+  const int el = M.color_elem[color_begin + slot];
+  const GfPatchDesc P = M.patches[M.elem_patch[el]];
+  const int eu = M.elem_eu[el], ev = M.elem_ev[el];
+  const int su = P.span_u_off + eu, sv = P.span_v_off + ev;
+  const int I0 = M.first_cp_u[su], J0 = M.first_cp_v[sv];
+  const int ncp = P.n_u * P.n_v;
+  const double area = M.span_h_u[su] * M.span_h_v[sv];
+  const int nq = M.nq;
+  const int half = lane >> 4, an = lane & 15;
+
+  if (lane < 16) {
+    const int lu = lane & 3, lv = lane >> 2;
+    const int I = I0 + lu, J = J0 + lv;
+    const int cpl = I + J * P.n_u;
+    const double4 c = reinterpret_cast<const double4*>(M.cp)[P.cp_off + cpl];
+    S.Xc[lane][0] = c.x; S.Xc[lane][1] = c.y; S.Xc[lane][2] = c.z; S.Xc[lane][3] = c.w;
+    const double* up = M.u + P.dof_off + cpl;
+    S.uc[lane][0] = up[0]; S.uc[lane][1] = up[ncp]; S.uc[lane][2] = up[2 * (size_t)ncp];
+    const int Ilo = M.cp_lo_u[P.cpd_u_off + I], Ihi = M.cp_hi_u[P.cpd_u_off + I];
+    const int Jlo = M.cp_lo_v[P.cpd_v_off + J], Jhi = M.cp_hi_v[P.cpd_v_off + J];
+    S.ninfo[lane][0] = cpl; S.ninfo[lane][1] = I; S.ninfo[lane][2] = J;
+    S.ninfo[lane][3] = Ilo; S.ninfo[lane][4] = Ihi - Ilo + 1; S.ninfo[lane][5] = Jlo;
+    S.ninfo[lane][6] = (Ihi - Ilo + 1) * (Jhi - Jlo + 1);
+    S.ninfo[lane][7] = M.row_nlow[P.cp_off + cpl];
+  }
+  int nt = 1;
+  if (P.th_kind == GF_TH_LINEAR) nt = 4; else if (P.th_kind == GF_TH_IGA) nt = 16;
+  if (lane < nt) {
+    int td;
+    if (P.th_kind == GF_TH_CONST) td = 0;
+    else if (P.th_kind == GF_TH_LINEAR) td = (eu + (lane & 1)) + (ev + (lane >> 1)) * (P.neu + 1);
+    else td = (I0 + (lane & 3)) + (J0 + (lane >> 2)) * P.n_u;
+    S.the[lane] = M.theta[P.th_off + td];
+  }
+  __syncwarp();
+
+  double acc[72];
+#pragma unroll
+  for (int i = 0; i < 72; ++i) acc[i] = 0.0;
+  double racc0 = 0.0, racc1 = 0.0, wsum = 0.0, vsum = 0.0;
+  const int ag = lane >> 3, bg = lane & 7;
+  const double* tu = M.tab_u + (size_t)su * nq * 12;
+  const double* tv = M.tab_v + (size_t)sv * nq * 12;
+
+  for (int q0 = 0; q0 < nq; q0 += 2) {
+    // this half's quadrature point (the second half idles with zero weight on an odd tail)
+    const bool valid = (q0 + half) < nq;
+    const int q = valid ? q0 + half : q0;
+    // ---- A. basis of both points (lanes 0..15: point q0, lanes 16..31: point q0+1) ----
+    {
+      const int lu = an & 3, lv = an >> 2;
+      const double* a = tu + q * 12;
+      const double* b = tv + q * 12;
+      const double u0 = a[lu], u1 = a[4 + lu], u2 = a[8 + lu];
+      const double v0 = b[lv], v1 = b[4 + lv], v2 = b[8 + lv];
+      double N = u0 * v0, Nu = u1 * v0, Nv = u0 * v1, Nuu = u2 * v0, Nvv = u0 * v2, Nuv = u1 * v1;
+      const double nraw = N;
+      if (P.rational) {
+        const double w = S.Xc[an][3];
+        double W = N * w, Wu = Nu * w, Wv = Nv * w, Wuu = Nuu * w, Wvv = Nvv * w, Wuv = Nuv * w;
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) {
+          W += __shfl_xor_sync(0xffffffffu, W, o);
+          Wu += __shfl_xor_sync(0xffffffffu, Wu, o);
+          Wv += __shfl_xor_sync(0xffffffffu, Wv, o);
+          Wuu += __shfl_xor_sync(0xffffffffu, Wuu, o);
+          Wvv += __shfl_xor_sync(0xffffffffu, Wvv, o);
+          Wuv += __shfl_xor_sync(0xffffffffu, Wuv, o);
+        }
+        const double iW = 1.0 / W;
+        const double f = N * iW;
+        const double fu = (Nu - f * Wu) * iW;
+        const double fv = (Nv - f * Wv) * iW;
+        const double fuu = (Nuu - 2.0 * fu * Wu - f * Wuu) * iW;
+        const double fvv = (Nvv - 2.0 * fv * Wv - f * Wvv) * iW;
+        const double fuv = (Nuv - fu * Wv - fv * Wu - f * Wuv) * iW;
+        N = f; Nu = fu; Nv = fv; Nuu = fuu; Nvv = fvv; Nuv = fuv;
+      }
+      S.Phi[half][0][an] = N; S.Phi[half][1][an] = Nu; S.Phi[half][2][an] = Nv;
+      S.Phi[half][3][an] = Nuu; S.Phi[half][4][an] = Nvv; S.Phi[half][5][an] = Nuv;
+      if (P.th_kind == GF_TH_IGA) S.tw[half][an] = nraw;
+      else if (P.th_kind == GF_TH_LINEAR) { if (an < 4) S.tw[half][an] = M.tw_lin[q * 4 + an]; }
+      else if (an == 0) S.tw[half][0] = 1.0;
+    }
+    __syncwarp();
+    // covariant vectors and thickness of both points: two rounds of 31 dot products
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double val = 0.0;
+      if (lane < 15) {
+        const int k = lane / 3 + 1, c = lane % 3;
+#pragma unroll
+        for (int a = 0; a < 16; ++a) val = fma(S.Phi[h][k][a], S.Xc[a][c], val);
+      } else if (lane == 15) {
+        for (int m = 0; m < nt; ++m) val = fma(S.tw[h][m], S.the[m], val);
+      } else if (lane < 31) {
+        const int k = (lane - 16) / 3 + 1, c = (lane - 16) % 3;
+#pragma unroll
+        for (int a = 0; a < 16; ++a) val = fma(S.Phi[h][k][a], S.uc[a][c], val);
+      }
+      S.g[h][lane] = val;
+    }
+    __syncwarp();
+    // ---- B. first variation; lane (half, d): direction d of point `half` ----
+    {
+      double gXd[15];
+      Dual gu[15], grad[15], e;
+#pragma unroll
+      for (int k = 0; k < 15; ++k) {
+        gXd[k] = S.g[half][k];
+        gu[k] = Dual(S.g[half][16 + k], (an == k) ? 1.0 : 0.0);
+      }
+      KlRef<double> R;
+      kl_reference<double>(gXd, P.E, P.nu, R);
+      kl_shell_point_fixed_ref<Dual>(gXd, R, gu, Dual(S.g[half][15]), e, grad);
+      if (an < 15) {
+#pragma unroll
+        for (int m = 0; m < 15; ++m) S.Hc[half][m][an] = grad[m].d;
+      } else {
+#pragma unroll
+        for (int m = 0; m < 15; ++m) S.Gv[half][m] = grad[m].v;
+        S.Gv[half][15] = R.J;
+        S.Ev[half] = e.v;
+      }
+    }
+    __syncwarp();
+    // ---- C. contraction, one point after the other, all 32 lanes ----
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      if (q0 + h >= nq) break;
+      const double wq = M.qw[q0 + h] * area;
+      for (int o = lane; o < 720; o += 32) {
+        const int m = o / 48, cb = o - m * 48;
+        const int b = cb / 3, j = cb - 3 * b;
+        double s = 0.0;
+#pragma unroll
+        for (int l = 0; l < 5; ++l) s = fma(S.Hc[h][m][l * 3 + j], S.Phi[h][1 + l][b], s);
+        S.G[m][cb] = wq * s;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        double ph[4];
+#pragma unroll
+        for (int aa = 0; aa < 4; ++aa) ph[aa] = S.Phi[h][1 + k][4 * ag + aa];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          double gg[6];
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) gg[cc] = S.G[3 * k + i][6 * bg + cc];
+#pragma unroll
+          for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc)
+              acc[(i * 4 + aa) * 6 + cc] = fma(ph[aa], gg[cc], acc[(i * 4 + aa) * 6 + cc]);
+        }
+      }
+      {
+        const int i0 = half ? 2 : 0;
+        double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          r0 = fma(S.Phi[h][1 + k][an], S.Gv[h][3 * k + i0], r0);
+          r1 = fma(S.Phi[h][1 + k][an], S.Gv[h][3 * k + 1], r1);
+        }
+        const double Jv = S.Gv[h][15];
+        const double jf = Jv * S.Phi[h][0][an];
+        racc0 += wq * (r0 - jf * P.f[i0]);
+        racc1 += wq * (r1 - jf * P.f[1]);
+        wsum += wq * S.Ev[h];
+        vsum += wq * Jv * S.g[h][15];
+      }
+      __syncwarp();
+    }
+  }
+
+  const size_t dof0 = (size_t)P.dof_off;
+  if (what & GF_OUT_K) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int aa = 0; aa < 4; ++aa) {
+        const int a = 4 * ag + aa;
+        const int* na = S.ninfo[a];
+        const size_t row = dof0 + (size_t)i * ncp + na[0];
+        const bool rbc = M.bc[row];
+        const int64_t base = M.K.indptr[row] + na[7];
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) {
+          const int cb = 6 * bg + cc, b = cb / 3, j = cb - 3 * b;
+          const int* nb = S.ninfo[b];
+          const size_t col = dof0 + (size_t)j * ncp + nb[0];
+          if (rbc || M.bc[col]) continue;
+          const int64_t pos = base + (int64_t)j * na[6] + (nb[2] - na[5]) * na[4] + (nb[1] - na[3]);
+          M.K.vals[pos] += acc[(i * 4 + aa) * 6 + cc];
+        }
+      }
+  }
+  if (what & GF_OUT_R) {
+    const int cpl = S.ninfo[an][0];
+    if (half == 0) { O.R[dof0 + cpl] += racc0; O.R[dof0 + ncp + cpl] += racc1; }
+    else O.R[dof0 + 2 * (size_t)ncp + cpl] += racc0;
+  }
+  if (what & GF_OUT_W) {
+    if (lane == 0) { O.WV[2 * (size_t)el] = wsum; O.WV[2 * (size_t)el + 1] = vsum; }
+  }
+}
+
+static int launch_k2(const GfModel* m, int what, const GfShellOut* out, cudaStream_t st) {
+  const size_t smem = 4 * sizeof(WarpSmemK2);
+  cudaError_t e = cudaFuncSetAttribute(k_shell_k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(k_shell_k2)");
+  for (int c = 0; c < m->num_colors; ++c) {
+    const int b = m->color_ptr_h[c], n = m->color_ptr_h[c + 1] - b;
+    if (n <= 0) continue;
+    k_shell_k2<<<(n + 3) / 4, 128, smem, st>>>(*m, *out, what, b, n);
+    count_launch(1);
+  }
+  count_launch(-1);
+  return check_launch("k_shell_k2");
+}
 }  // namespace gf
 
 extern "C" int gf_shell_assemble(const GfModel* m, int what, const GfShellOut* out, void* stream) {
@@ -477,7 +727,8 @@ extern "C" int gf_shell_assemble(const GfModel* m, int what, const GfShellOut* o
   if (what & (GF_OUT_R | GF_OUT_K | GF_OUT_W)) {
     if ((what & GF_OUT_R) && !out->R) return gf::set_error(GF_ERR_BADARG, "GF_OUT_R without out->R");
     if ((what & GF_OUT_W) && !out->WV) return gf::set_error(GF_ERR_BADARG, "GF_OUT_W without out->WV");
-    rc = gf::launch_mode<gf::MODE_K>(m, what, out, st);
+    static const bool v1 = getenv("GF_SHELL_V1") != nullptr;   // keep the one-point-per-pass kernel reachable
+    rc = v1 ? gf::launch_mode<gf::MODE_K>(m, what, out, st) : gf::launch_k2(m, what, out, st);
     if (rc) return rc;
   }
   if (what & GF_OUT_P) { rc = gf::launch_mode<gf::MODE_P>(m, what, out, st); if (rc) return rc; }

@@ -81,6 +81,68 @@ template <class S> GF_HD void st3(S* p, const V3<S>& a) { p[0] = a.x; p[1] = a.y
 // grad[15] = d e / d gu  (first variation w.r.t. the displacement derivatives,
 // which equals d e / d gx at fixed reference configuration).
 // ---------------------------------------------------------------------------
+template <class S> GF_HD V3<S> lift(const V3<S>& a) { return a; }
+GF_HD V3<Dual> lift_d(const V3<double>& a) { return mk<Dual>(Dual(a.x), Dual(a.y), Dual(a.z)); }
+
+// Reference-configuration quantities (depend on g_X only).
+template <class S> struct KlRef { S J, A11, A22, A12, B11, B22, B12, D11, D12, D13, D22, D23, D33; };
+
+template <class S>
+GF_HD void kl_reference(const S* gX, double E, double nu, KlRef<S>& R) {
+  const V3<S> X1 = ld3(gX), X2 = ld3(gX + 3), X11 = ld3(gX + 6), X22 = ld3(gX + 9), X12 = ld3(gX + 12);
+  const V3<S> Nr = cross(X1, X2);
+  const S det = dot(Nr, Nr);
+  R.J = gf_sqrt(det);
+  const S iJ = 1.0 / R.J;
+  const V3<S> A3 = scal(iJ, Nr);
+  R.A11 = dot(X1, X1); R.A22 = dot(X2, X2); R.A12 = dot(X1, X2);
+  R.B11 = dot(X11, A3); R.B22 = dot(X22, A3); R.B12 = dot(X12, A3);
+  const S idet = 1.0 / det;
+  const S c11 = R.A22 * idet, c22 = R.A11 * idet, c12 = -(R.A12 * idet);
+  const double C = E / (1.0 - nu * nu);
+  R.D11 = C * (c11 * c11); R.D22 = C * (c22 * c22);
+  R.D12 = C * (nu * (c11 * c22) + (1.0 - nu) * (c12 * c12));
+  R.D13 = C * (c11 * c12); R.D23 = C * (c22 * c12);
+  R.D33 = (0.5 * C) * ((1.0 - nu) * (c11 * c22) + (1.0 + nu) * (c12 * c12));
+}
+
+// Deformed configuration with PLAIN reference data (directions in g_u and t only):
+// the tangent and dR/dt passes use this -- the reference part costs no dual arithmetic.
+template <class S>
+GF_HD void kl_shell_point_fixed_ref(const double* gXd, const KlRef<double>& R, const S* gu, S t,
+                                    S& e, S* grad) {
+  S gx[15];
+#pragma unroll
+  for (int k = 0; k < 15; ++k) gx[k] = gXd[k] + gu[k];
+  const V3<S> x1 = ld3(gx), x2 = ld3(gx + 3), x11 = ld3(gx + 6), x22 = ld3(gx + 9), x12 = ld3(gx + 12);
+  const V3<S> n = cross(x1, x2);
+  const S j = gf_sqrt(dot(n, n));
+  const S ij = 1.0 / j;
+  const V3<S> a3 = scal(ij, n);
+  const S a11 = dot(x1, x1), a22 = dot(x2, x2), a12 = dot(x1, x2);
+  const S b11 = dot(x11, a3), b22 = dot(x22, a3), b12 = dot(x12, a3);
+  const S e0 = 0.5 * (a11 - R.A11), e1 = 0.5 * (a22 - R.A22), e2 = a12 - R.A12;
+  const S k0 = R.B11 - b11, k1 = R.B22 - b22, k2 = 2.0 * (R.B12 - b12);
+  const S tb = (t * t * t) * (1.0 / 12.0);
+  const S n0 = t * (R.D11 * e0 + R.D12 * e1 + R.D13 * e2);
+  const S n1 = t * (R.D12 * e0 + R.D22 * e1 + R.D23 * e2);
+  const S n2 = t * (R.D13 * e0 + R.D23 * e1 + R.D33 * e2);
+  const S m0 = tb * (R.D11 * k0 + R.D12 * k1 + R.D13 * k2);
+  const S m1 = tb * (R.D12 * k0 + R.D22 * k1 + R.D23 * k2);
+  const S m2 = tb * (R.D13 * k0 + R.D23 * k1 + R.D33 * k2);
+  e = (0.5 * R.J) * (e0 * n0 + e1 * n1 + e2 * n2 + k0 * m0 + k1 * m1 + k2 * m2);
+  const V3<S> hm = scal(m0, x11) + scal(m1, x22) + scal(2.0 * m2, x12);
+  const V3<S> hp = hm - scal(dot(hm, a3), a3);
+  const S Jj = R.J * ij;
+  const V3<S> g1 = scal(S(R.J), scal(n0, x1) + scal(n2, x2)) - scal(Jj, cross(x2, hp));
+  const V3<S> g2 = scal(S(R.J), scal(n1, x2) + scal(n2, x1)) - scal(Jj, cross(hp, x1));
+  st3(grad, g1);
+  st3(grad + 3, g2);
+  st3(grad + 6, scal(-(R.J * m0), a3));
+  st3(grad + 9, scal(-(R.J * m1), a3));
+  st3(grad + 12, scal(-(2.0 * (R.J * m2)), a3));
+}
+
 template <class S>
 GF_HD void kl_shell_point(const S* gX, const S* gu, S t, double E, double nu,
                           S& e, S& J, S* grad) {
