@@ -39,6 +39,12 @@ __device__ __forceinline__ double sum_partials(const double* p, int n, int strid
 }
 
 // ---------------------------------------------------------------- SpMV ------
+// streaming loads for the matrix (read once), cached loads for the gathered vector
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ int ld_stream(const int32_t* p) { return __ldcs(p); }
+
+// Warp per row; the row's chunks of 32 entries are loaded four at a time before any
+// FMA so that 4 x (8 + 4) bytes per lane are in flight (rows of K hold ~147 entries).
 __global__ void __launch_bounds__(256)
 k_spmv(GfCsr A, const double* __restrict__ x, double* __restrict__ y, double alpha, double beta,
        const double* __restrict__ dotv, double* __restrict__ partial) {
@@ -49,10 +55,26 @@ k_spmv(GfCsr A, const double* __restrict__ x, double* __restrict__ y, double alp
   double dacc = 0.0;
   for (; row < A.nrows; row += nwarps) {
     const int64_t s = A.indptr[row], e = A.indptr[row + 1];
-    double sum = 0.0;
-    for (int64_t k = s + lane; k < e; k += 32)
-      sum = fma(A.vals[k], __ldg(x + A.indices[k]), sum);
-    sum = warp_sum(sum);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int64_t k = s + lane;
+    for (; k + 96 < e; k += 128) {
+      const int c0 = ld_stream(A.indices + k), c1 = ld_stream(A.indices + k + 32),
+                c2 = ld_stream(A.indices + k + 64), c3 = ld_stream(A.indices + k + 96);
+      const double v0 = ld_stream(A.vals + k), v1 = ld_stream(A.vals + k + 32),
+                   v2 = ld_stream(A.vals + k + 64), v3 = ld_stream(A.vals + k + 96);
+      s0 = fma(v0, __ldg(x + c0), s0); s1 = fma(v1, __ldg(x + c1), s1);
+      s2 = fma(v2, __ldg(x + c2), s2); s3 = fma(v3, __ldg(x + c3), s3);
+    }
+    {   // tail: up to four guarded chunks, still loaded before use
+      const bool p0 = k < e, p1 = k + 32 < e, p2 = k + 64 < e, p3 = k + 96 < e;
+      const int c0 = p0 ? ld_stream(A.indices + k) : 0, c1 = p1 ? ld_stream(A.indices + k + 32) : 0,
+                c2 = p2 ? ld_stream(A.indices + k + 64) : 0, c3 = p3 ? ld_stream(A.indices + k + 96) : 0;
+      const double v0 = p0 ? ld_stream(A.vals + k) : 0.0, v1 = p1 ? ld_stream(A.vals + k + 32) : 0.0,
+                   v2 = p2 ? ld_stream(A.vals + k + 64) : 0.0, v3 = p3 ? ld_stream(A.vals + k + 96) : 0.0;
+      s0 = fma(v0, __ldg(x + c0), s0); s1 = fma(v1, __ldg(x + c1), s1);
+      s2 = fma(v2, __ldg(x + c2), s2); s3 = fma(v3, __ldg(x + c3), s3);
+    }
+    const double sum = warp_sum((s0 + s1) + (s2 + s3));
     if (lane == 0) {
       double v = alpha * sum;
       if (beta != 0.0) v = fma(beta, y[row], v);
@@ -88,7 +110,7 @@ k_spmv_t(GfCsr A, GfCsrT At, const double* __restrict__ x, double* __restrict__ 
 
 static int spmv_grid(int64_t nrows) {
   int64_t g = (nrows * 32 + 255) / 256;
-  if (g > MAX_PARTIAL) g = MAX_PARTIAL;
+  if (g > 888) g = 888;                       // 148 SMs x 6 resident CTAs of 256 threads: one full wave
   if (g < 1) g = 1;
   return (int)g;
 }

@@ -350,9 +350,9 @@ class OracleModel:
                 (self.patches[I.sB], I.connB[v], I.DB[v][:, 0:3, :])]
 
     # -------------------------------------------------------------- residual
-    def residual(self, apply_bcs=True):
+    def residual(self, apply_bcs=True, shell=True, penalty=True, const_loads=True):
         R = np.zeros(self.N)
-        for P in self.patches:
+        for P in (self.patches if shell else []):
             for sel in self._chunks(P):
                 e, J, uq = self._shell_jets(P, sel, False)
                 ne = len(sel)
@@ -363,22 +363,23 @@ class OracleModel:
                 Re -= np.einsum("eqa,eq,c->eac", P.D[sel][:, :, 0], Jw, P.body_force)
                 for c in range(3):
                     np.add.at(R, P.off + c * P.ncp + P.conn[sel], Re[:, :, c])
-        for I in self.interfaces:
+        for I in (self.interfaces if penalty else []):
             e = self._penalty_jets(I, False)
             for side, (P, conn, coef) in enumerate(self._penalty_B(I)):
                 g = e.g[:, 9 * side:9 * side + 9].reshape(-1, 3, 3)  # (n,kind,comp)
                 Re = np.einsum("qka,qkc->qac", coef, g)
                 for c in range(3):
                     np.add.at(R, P.off + c * P.ncp + conn, Re[:, :, c])
-        R += self.f_const
+        if const_loads:
+            R += self.f_const
         if apply_bcs:
             R[self.bc_global] = 0.0
         return R
 
     # ------------------------------------------------------------- stiffness
-    def stiffness(self, apply_bcs=True):
+    def stiffness(self, apply_bcs=True, shell=True, penalty=True):
         rows, cols, vals = [], [], []
-        for P in self.patches:
+        for P in (self.patches if shell else []):
             for sel in self._chunks(P):
                 e, J, uq = self._shell_jets(P, sel, False)
                 ne = len(sel)
@@ -390,7 +391,7 @@ class OracleModel:
                 rows.append(np.broadcast_to(r[:, :, :, None, None], Ke.shape).ravel())
                 cols.append(np.broadcast_to(r[:, None, None, :, :], Ke.shape).ravel())
                 vals.append(Ke.ravel())
-        for I in self.interfaces:
+        for I in (self.interfaces if penalty else []):
             e = self._penalty_jets(I, False)
             Bs = self._penalty_B(I)
             for s0, (P0, conn0, coef0) in enumerate(Bs):
@@ -409,6 +410,8 @@ class OracleModel:
 
     @staticmethod
     def _to_csr(rows, cols, vals, shape):
+        if not rows:
+            return sp.csr_matrix(shape)
         A = sp.coo_matrix((np.concatenate(vals),
                            (np.concatenate(rows), np.concatenate(cols))), shape=shape).tocsr()
         A.sum_duplicates()
@@ -442,7 +445,7 @@ class OracleModel:
         surf_inds; columns = concatenated scalar CP dofs of those patches."""
         return self.dRdCP_fields([field], surf_inds, apply_bcs)[0]
 
-    def dRdCP_fields(self, fields, surf_inds=None, apply_bcs=True):
+    def dRdCP_fields(self, fields, surf_inds=None, apply_bcs=True, shell=True, penalty=True):
         """Same for several fields sharing one AD pass (all fields on the same
         patch list)."""
         if surf_inds is None:
@@ -456,7 +459,7 @@ class OracleModel:
         nf = len(fields)
         rows, cols = [], []
         vals = [[] for _ in fields]
-        for s in surf_inds:
+        for s in (surf_inds if shell else []):
             P = self.patches[s]
             for sel in self._chunks(P):
                 e, J, uq = self._shell_jets(P, sel, True)
@@ -479,7 +482,7 @@ class OracleModel:
                     Ae -= np.einsum("eqa,i,eql,eqlb->eaib", P.D[sel][:, :, 0], P.body_force, dJ, D5,
                                     optimize=True)
                     vals[k].append(Ae.ravel())
-        for I in self.interfaces:
+        for I in (self.interfaces if penalty else []):
             if I.sA not in coloff and I.sB not in coloff:
                 continue
             e = self._penalty_jets(I, True)
