@@ -75,7 +75,7 @@ class GfSchwarz(C.Structure):
                 ("n_pad", c_vp), ("nbr", c_vp), ("off_j", c_vp), ("mbj", c_vp), ("rlen", c_vp), ("off_col", c_vp),
                 ("step_mb_h", c_vp), ("off_y", c_vp), ("off_inv", c_vp),
                 ("glob", c_vp), ("gs", c_vp), ("ls", c_vp), ("off_g", c_vp), ("zptr", c_vp), ("zsrc", c_vp),
-                ("band", c_vp), ("invd", c_vp), ("y", c_vp), ("s", c_vp), ("barrier", c_vp), ("flag", c_vp)]
+                ("band", c_vp), ("band32", c_vp), ("invd", c_vp), ("y", c_vp), ("s", c_vp), ("barrier", c_vp), ("flag", c_vp)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_int, c_vp)

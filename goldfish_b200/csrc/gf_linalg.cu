@@ -7,6 +7,7 @@
 // one CG).  All reductions use fixed trees over a fixed grid: results are
 // bit-reproducible from run to run.
 #include "gf_common.cuh"
+#include <stdlib.h>
 
 namespace gf {
 
@@ -40,14 +41,43 @@ __device__ __forceinline__ double sum_partials(const double* p, int n, int strid
 
 // ---------------------------------------------------------------- SpMV ------
 // streaming loads for the matrix (read once), cached loads for the gathered vector
-__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
-__device__ __forceinline__ int ld_stream(const int32_t* p) { return __ldcs(p); }
+template <int CS> __device__ __forceinline__ double ld_m(const double* p) { return CS ? __ldcs(p) : __ldg(p); }
+template <int CS> __device__ __forceinline__ int ld_m(const int32_t* p) { return CS ? __ldcs(p) : __ldg(p); }
+#define ld_stream ld_m<CS>
+
+// simple variant: one chunk of 32 entries per loop trip
+__global__ void __launch_bounds__(256)
+k_spmv_simple(GfCsr A, const double* __restrict__ x, double* __restrict__ y, double alpha, double beta,
+              const double* __restrict__ dotv, double* __restrict__ partial) {
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  double dacc = 0.0;
+  for (; row < A.nrows; row += nwarps) {
+    const int64_t s = A.indptr[row], e = A.indptr[row + 1];
+    double sum = 0.0;
+    for (int64_t k = s + lane; k < e; k += 32) sum = fma(A.vals[k], __ldg(x + A.indices[k]), sum);
+    sum = warp_sum(sum);
+    if (lane == 0) {
+      double v = alpha * sum;
+      if (beta != 0.0) v = fma(beta, y[row], v);
+      y[row] = v;
+      if (dotv) dacc = fma(dotv[row], v, dacc);
+    }
+  }
+  if (partial) {
+    const double b = block_sum(dacc, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = b;
+  }
+}
 
 // Warp per row; the row's chunks of 32 entries are loaded four at a time before any
 // FMA so that 4 x (8 + 4) bytes per lane are in flight (rows of K hold ~147 entries).
+template <int CS>
 __global__ void __launch_bounds__(256)
-k_spmv(GfCsr A, const double* __restrict__ x, double* __restrict__ y, double alpha, double beta,
-       const double* __restrict__ dotv, double* __restrict__ partial) {
+k_spmv_u4(GfCsr A, const double* __restrict__ x, double* __restrict__ y, double alpha, double beta,
+          const double* __restrict__ dotv, double* __restrict__ partial) {
   __shared__ double sh[32];
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -108,9 +138,26 @@ k_spmv_t(GfCsr A, GfCsrT At, const double* __restrict__ x, double* __restrict__ 
   }
 }
 
+#undef ld_stream
+static int g_spmv_variant = -1, g_spmv_grid = 1024;
+static void spmv_config() {
+  if (g_spmv_variant >= 0) return;
+  g_spmv_variant = 0;
+  if (const char* v = getenv("GF_SPMV_VARIANT")) g_spmv_variant = atoi(v);
+  if (const char* v = getenv("GF_SPMV_GRID")) g_spmv_grid = atoi(v);
+  if (g_spmv_grid > MAX_PARTIAL) g_spmv_grid = MAX_PARTIAL;
+}
+static void launch_spmv(int grid, cudaStream_t st, const GfCsr& A, const double* x, double* y, double alpha,
+                        double beta, const double* dotv, double* partial) {
+  spmv_config();
+  if (g_spmv_variant == 1) k_spmv_u4<1><<<grid, 256, 0, st>>>(A, x, y, alpha, beta, dotv, partial);
+  else if (g_spmv_variant == 2) k_spmv_u4<0><<<grid, 256, 0, st>>>(A, x, y, alpha, beta, dotv, partial);
+  else k_spmv_simple<<<grid, 256, 0, st>>>(A, x, y, alpha, beta, dotv, partial);
+}
 static int spmv_grid(int64_t nrows) {
+  spmv_config();
   int64_t g = (nrows * 32 + 255) / 256;
-  if (g > 888) g = 888;                       // 148 SMs x 6 resident CTAs of 256 threads: one full wave
+  if (g > g_spmv_grid) g = g_spmv_grid;
   if (g < 1) g = 1;
   return (int)g;
 }
@@ -244,7 +291,7 @@ using namespace gf;
 extern "C" int gf_spmv(const GfCsr* A, const double* x, double* y, double alpha, double beta, void* stream) {
   if (!A || !x || !y) return set_error(GF_ERR_BADARG, "gf_spmv: null argument");
   if (A->nrows == 0) return GF_OK;
-  k_spmv<<<spmv_grid(A->nrows), 256, 0, (cudaStream_t)stream>>>(*A, x, y, alpha, beta, nullptr, nullptr);
+  launch_spmv(spmv_grid(A->nrows), (cudaStream_t)stream, *A, x, y, alpha, beta, nullptr, nullptr);
   return check_launch("k_spmv");
 }
 
@@ -367,7 +414,7 @@ extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWor
     const int parity = it & 1;
     int npart1 = gs;
     if (!sharded) {
-      k_spmv<<<gs, 256, 0, st>>>(*A, w->p, w->Ap, 1.0, 0.0, w->p, part1);
+      launch_spmv(gs, st, *A, w->p, w->Ap, 1.0, 0.0, w->p, part1);
     } else {
       // owned rows only, then sum over ranks; every rank then holds the full A p and
       // computes the (identical) dot products itself -> no scalar all-reduce
@@ -377,7 +424,7 @@ extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWor
         const int64_t b0 = dist->ranges_h[2 * q], b1 = dist->ranges_h[2 * q + 1];
         if (b1 <= b0) continue;
         GfCsr sub = *A; sub.indptr = A->indptr + b0; sub.nrows = b1 - b0;
-        k_spmv<<<spmv_grid(sub.nrows), 256, 0, st>>>(sub, w->p, w->Ap + b0, 1.0, 0.0, nullptr, nullptr);
+        launch_spmv(spmv_grid(sub.nrows), st, sub, w->p, w->Ap + b0, 1.0, 0.0, nullptr, nullptr);
         count_launch(1);
       }
       if (dist->allreduce(0, dist->ctx)) return set_error(GF_ERR_CUDA, "all-reduce of A p failed");

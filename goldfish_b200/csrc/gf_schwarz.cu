@@ -280,12 +280,24 @@ k_sw_convert_diag(GfSchwarz S) {
     for (int y = 0; y < 4; ++y) inv[(r0 + x) * NB + c0 + y] = acc[x][y];
 }
 
+// The sweeps are bound by streaming the factor from HBM (it is read twice per
+// preconditioner application), so the solve-form panels are also kept in FP32:
+// a fixed, symmetric (M forward, M^T backward) and positive definite operator,
+// which is all CG needs from a preconditioner.  Arithmetic stays FP64.
+__global__ void k_sw_to_f32(const double* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = (float)src[i];
+}
+__device__ __forceinline__ const float* sw_block32(const GfSchwarz& S, int i, int j, int k) {
+  return S.band32 + S.off_col[S.off_j[i] + j] + (size_t)k * NB2;
+}
+
 // one block GEMV of the forward sweep with the block already in registers:
 // warp w owns rows 8w..8w+7, lanes run along the row (coalesced 512-B rows)
-__device__ __forceinline__ void load_blk(const double* __restrict__ L, int w, int lane, double (&Lr)[16]) {
-  const double* p = L + (size_t)(w * 8) * NB;
+__device__ __forceinline__ void load_blk(const float* __restrict__ L, int w, int lane, double (&Lr)[16]) {
+  const float* p = L + (size_t)(w * 8) * NB;
 #pragma unroll
-  for (int rr = 0; rr < 8; ++rr) { Lr[2 * rr] = __ldcs(p + rr * NB + lane); Lr[2 * rr + 1] = __ldcs(p + rr * NB + lane + 32); }
+  for (int rr = 0; rr < 8; ++rr) { Lr[2 * rr] = (double)__ldcs(p + rr * NB + lane); Lr[2 * rr + 1] = (double)__ldcs(p + rr * NB + lane + 32); }
 }
 
 // Fine patch blocks and (optionally) the single coarse block run in ONE cooperative
@@ -313,11 +325,11 @@ k_sw_solve(GfSchwarz Sf, int G_f, int first_block, int nf, GfSchwarz Sc, int G_c
 
   // ---------------- forward: y_{j+k} -= M(j+k, j) y_j ----------------
   bool have = (nbr > 0 && k0 <= mbj[0]);
-  if (have) load_blk(sw_block(S, i, 0, k0), w, lane, Lr);
+  if (have) load_blk(sw_block32(S, i, 0, k0), w, lane, Lr);
   for (int j = 0; j < nbr; ++j) {
     const double x0 = __ldcg(y + (size_t)j * NB + lane), x1 = __ldcg(y + (size_t)j * NB + lane + 32);
     for (int k = k0; k <= mbj[j]; k += G) {
-      if (k != k0) load_blk(sw_block(S, i, j, k), w, lane, Lr);
+      if (k != k0) load_blk(sw_block32(S, i, j, k), w, lane, Lr);
       double sacc[8];
 #pragma unroll
       for (int rr = 0; rr < 8; ++rr) sacc[rr] = warp_sum(Lr[2 * rr] * x0 + Lr[2 * rr + 1] * x1);
@@ -330,7 +342,7 @@ k_sw_solve(GfSchwarz Sf, int G_f, int first_block, int nf, GfSchwarz Sc, int G_c
       }
     }
     // prefetch the first block of the next step while waiting at the barrier
-    if (j + 1 < nbr && k0 <= mbj[j + 1]) load_blk(sw_block(S, i, j + 1, k0), w, lane, Lr);
+    if (j + 1 < nbr && k0 <= mbj[j + 1]) load_blk(sw_block32(S, i, j + 1, k0), w, lane, Lr);
     ++step;
     group_barrier(cnt, step * (unsigned)G);
   }
@@ -358,13 +370,16 @@ k_sw_solve(GfSchwarz Sf, int G_f, int first_block, int nf, GfSchwarz Sc, int G_c
     if (tid < NB) xs[tid] = __ldcg(y + (size_t)j * NB + tid) - __ldcg(sv + (size_t)j * NB + tid);
     __syncthreads();
     for (int k = k0; k <= rlen[j]; k += G) {
-      const double* L = sw_block(S, i, j - k, k) + (size_t)(w * 8) * NB;
+      const float* L = sw_block32(S, i, j - k, k) + (size_t)(w * 8) * NB;
+      float l0[8], l1[8];
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) { l0[rr] = __ldcs(L + rr * NB + lane); l1[rr] = __ldcs(L + rr * NB + lane + 32); }
       double a0 = 0.0, a1 = 0.0;
 #pragma unroll
       for (int rr = 0; rr < 8; ++rr) {
         const double xr = xs[w * 8 + rr];
-        a0 = fma(__ldcs(L + rr * NB + lane), xr, a0);
-        a1 = fma(__ldcs(L + rr * NB + lane + 32), xr, a1);
+        a0 = fma((double)l0[rr], xr, a0);
+        a1 = fma((double)l1[rr], xr, a1);
       }
       __syncthreads();
       red[w][lane] = a0; red[w][lane + 32] = a1;
@@ -431,7 +446,8 @@ extern "C" int gf_schwarz_factor(const GfSchwarz* S, const GfCsr* K, void* strea
   k_sw_invert<<<dim3(S->max_nbr, S->nblocks), 256, smem, st>>>(*S);
   if (S->max_mb > 0) k_sw_convert_panel<<<dim3(S->max_mb, S->max_nbr, S->nblocks), 256, smem, st>>>(*S);
   k_sw_convert_diag<<<dim3(S->max_nbr, S->nblocks), 256, smem, st>>>(*S);
-  count_launch(2);
+  k_sw_to_f32<<<2048, 256, 0, st>>>(S->band, S->band32, S->band_len);
+  count_launch(3);
   int flag = 0;
   e = cudaMemcpyAsync(&flag, S->flag, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -446,6 +446,7 @@ class DeviceModel:
             t = {k: torch.from_numpy(np.ascontiguousarray(A[k])).to(dv)
                  for k in ("n_pad", "nbr", "off_j", "mbj", "rlen", "off_col", "off_y", "off_inv", "glob", "gs", "ls", "off_g", "zptr", "zsrc")}
             t["band"] = torch.zeros(A["band_len"], dtype=torch.float64, device=dv)
+            t["band32"] = torch.zeros(A["band_len"], dtype=torch.float32, device=dv)
             t["invd"] = torch.zeros(A["inv_len"], dtype=torch.float64, device=dv)
             t["y"] = torch.zeros(A["n_y"], dtype=torch.float64, device=dv)
             t["s"] = torch.zeros(A["n_y"], dtype=torch.float64, device=dv)
@@ -458,7 +459,7 @@ class DeviceModel:
             s.ctas_per_block = 0          # chosen in gf_schwarz_apply from the SM count and panel height
             s.n_y, s.band_len = A["n_y"], A["band_len"]
             for k in ("n_pad", "nbr", "off_j", "mbj", "rlen", "off_col", "off_y", "off_inv", "glob", "gs", "ls", "off_g", "zptr", "zsrc",
-                      "band", "invd", "y", "s", "barrier", "flag"):
+                      "band", "band32", "invd", "y", "s", "barrier", "flag"):
                 setattr(s, k, _ptr(t[k]))
             s.step_mb_h = step_mb.ctypes.data_as(C.c_void_p)
             self._sw = (s, t, step_mb, A)

@@ -199,6 +199,7 @@ typedef struct GfSchwarz {
   const int64_t* zptr;            /* [N+1] prolongation gather                        */
   const int64_t* zsrc;            /* [..] indices into y                              */
   double* band;                   /* factor storage: nb x nb blocks                   */
+  float* band32;                  /* FP32 copy of the solve-form panels (streamed by the sweeps) */
   double* invd;                   /* inverses of the diagonal factor blocks           */
   double* y;                      /* [n_y] block-local vectors                        */
   double* s;                      /* [n_y] backward-sweep accumulators                */
