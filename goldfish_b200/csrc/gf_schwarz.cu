@@ -18,6 +18,7 @@
 //   z = sum_i R_i^T (L_i L_i^T)^-1 R_i r  assembled by a fixed-order gather.
 #include "gf_common.cuh"
 #include <stdlib.h>
+#include <cuda_pipeline.h>
 
 namespace gf {
 
@@ -292,16 +293,32 @@ __device__ __forceinline__ const float* sw_block32(const GfSchwarz& S, int i, in
   return S.band32 + S.off_col[S.off_j[i] + j] + (size_t)k * NB2;
 }
 
-// one block GEMV of the forward sweep with the block already in registers:
-// warp w owns rows 8w..8w+7, lanes run along the row (coalesced 512-B rows)
-__device__ __forceinline__ void load_blk(const float* __restrict__ L, int w, int lane, double (&Lr)[16]) {
-  const float* p = L + (size_t)(w * 8) * NB;
+constexpr int PF = 4;        // panel blocks of the NEXT step prefetched into shared memory per CTA
+constexpr int LDS = NB + 4;  // padded row stride (floats) of a prefetched block: 16-B aligned, conflict-light
+constexpr int PBLK = NB * LDS;
+
+// cp.async the CTA's first PF panel blocks of step `j` (forward: column panel j, backward:
+// row j of the factor) into shared memory; they land while the CTA waits at the group barrier.
+__device__ __forceinline__ void sw_prefetch(const GfSchwarz& S, int i, int j, int k0, int G, int kmax,
+                                            bool backward, float* pre) {
+  const int tid = threadIdx.x;
 #pragma unroll
-  for (int rr = 0; rr < 8; ++rr) { Lr[2 * rr] = (double)__ldcs(p + rr * NB + lane); Lr[2 * rr + 1] = (double)__ldcs(p + rr * NB + lane + 32); }
+  for (int t = 0; t < PF; ++t) {
+    const int k = k0 + t * G;
+    if (k > kmax) break;
+    const float* src = backward ? sw_block32(S, i, j - k, k) : sw_block32(S, i, j, k);
+    float* dst = pre + t * PBLK;
+#pragma unroll
+    for (int e = tid; e < NB2 / 4; e += 256)                // 16-byte chunks: row e/16, chunk e%16
+      __pipeline_memcpy_async(dst + (e >> 4) * LDS + (e & 15) * 4, src + e * 4, 16);
+  }
+  __pipeline_commit();
 }
 
-// Fine patch blocks and (optionally) the single coarse block run in ONE cooperative
-// launch: CTAs [0, nf*G) serve fine blocks first_block.., CTAs beyond serve the coarse block.
+// The sweeps stream the factor once forward and once backward; measured on B200 they were
+// bound by FP32->FP64 conversions (16/clk/SM) and FP64 shuffle reductions, not by HBM.  The
+// block GEMVs therefore run in FP32 (FFMA, x converted once per step, 4 threads per row /
+// column, 2-step reductions); results are accumulated into the FP64 vectors.
 __global__ void __launch_bounds__(256)
 k_sw_solve(GfSchwarz Sf, int G_f, int first_block, int nf, GfSchwarz Sc, int G_c) {
   const bool is_c = (int)blockIdx.x >= nf * G_f;
@@ -309,8 +326,10 @@ k_sw_solve(GfSchwarz Sf, int G_f, int first_block, int nf, GfSchwarz Sc, int G_c
   const int G = is_c ? G_c : G_f;
   const int bx = is_c ? (int)blockIdx.x - nf * G_f : (int)blockIdx.x;
   const int i = is_c ? 0 : first_block + bx / G, cta = bx % G;
+  extern __shared__ __align__(16) float pre[];     // [PF][64][LDS] floats
   __shared__ double xs[NB];
-  __shared__ double red[8][NB];
+  __shared__ __align__(16) float xf[NB];
+  __shared__ float red[4][NB];
   const int nbr = S.nbr[i];
   const int32_t* mbj = S.mbj + S.off_j[i];
   const int32_t* rlen = S.rlen + S.off_j[i];
@@ -320,33 +339,52 @@ k_sw_solve(GfSchwarz Sf, int G_f, int first_block, int nf, GfSchwarz Sc, int G_c
   unsigned* cnt = S.barrier + i;
   unsigned step = 0;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  double Lr[16];
-  const int k0 = 1 + cta;
+  const int dbg = S.ctas_per_block;               // timing experiments only: 1 = skip GEMVs, 2 = skip barriers
+  const int k0 = (dbg & 1) ? 1000000 : 1 + cta;
+  const int fr = tid >> 2, fq = tid & 3;           // forward: row fr, quarter fq (16 columns)
+  const int bc = tid & 63, bq = tid >> 6;          // backward: column bc, quarter bq (16 rows)
 
   // ---------------- forward: y_{j+k} -= M(j+k, j) y_j ----------------
-  bool have = (nbr > 0 && k0 <= mbj[0]);
-  if (have) load_blk(sw_block32(S, i, 0, k0), w, lane, Lr);
+  if (nbr > 0) sw_prefetch(S, i, 0, k0, G, mbj[0], false, pre);
   for (int j = 0; j < nbr; ++j) {
-    const double x0 = __ldcg(y + (size_t)j * NB + lane), x1 = __ldcg(y + (size_t)j * NB + lane + 32);
-    for (int k = k0; k <= mbj[j]; k += G) {
-      if (k != k0) load_blk(sw_block32(S, i, j, k), w, lane, Lr);
-      double sacc[8];
+    if (tid < NB) xf[tid] = (float)__ldcg(y + (size_t)j * NB + tid);
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    float xr[16];
 #pragma unroll
-      for (int rr = 0; rr < 8; ++rr) sacc[rr] = warp_sum(Lr[2 * rr] * x0 + Lr[2 * rr + 1] * x1);
-      if (lane < 8) {
-        double v = sacc[0];
-#pragma unroll
-        for (int rr = 1; rr < 8; ++rr) v = (lane == rr) ? sacc[rr] : v;
-        double* dst = y + (size_t)(j + k) * NB + w * 8 + lane;
-        __stcg(dst, __ldcg(dst) - v);
-      }
+    for (int c = 0; c < 16; c += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(xf + fq * 16 + c);
+      xr[c] = v.x; xr[c + 1] = v.y; xr[c + 2] = v.z; xr[c + 3] = v.w;
     }
-    // prefetch the first block of the next step while waiting at the barrier
-    if (j + 1 < nbr && k0 <= mbj[j + 1]) load_blk(sw_block32(S, i, j + 1, k0), w, lane, Lr);
+    int t = 0;
+    for (int k = k0; k <= mbj[j]; k += G, ++t) {
+      float a = 0.f;
+      if (t < PF) {
+        const float* p = pre + t * PBLK + fr * LDS + fq * 16;
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) {
+          const float4 m = *reinterpret_cast<const float4*>(p + c);
+          a = fmaf(m.x, xr[c], a); a = fmaf(m.y, xr[c + 1], a); a = fmaf(m.z, xr[c + 2], a); a = fmaf(m.w, xr[c + 3], a);
+        }
+      } else {
+        const float4* p = reinterpret_cast<const float4*>(sw_block32(S, i, j, k) + fr * NB + fq * 16);
+        const float4 m0 = __ldcs(p), m1 = __ldcs(p + 1), m2 = __ldcs(p + 2), m3 = __ldcs(p + 3);
+        a = m0.x * xr[0] + m0.y * xr[1] + m0.z * xr[2] + m0.w * xr[3] + m1.x * xr[4] + m1.y * xr[5] + m1.z * xr[6] + m1.w * xr[7]
+          + m2.x * xr[8] + m2.y * xr[9] + m2.z * xr[10] + m2.w * xr[11] + m3.x * xr[12] + m3.y * xr[13] + m3.z * xr[14] + m3.w * xr[15];
+      }
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      // fire-and-forget reduction: every entry receives at most one contribution per step and
+      // steps are separated by the group barrier, so the summation order is fixed.
+      if (fq == 0) atomicAdd(y + (size_t)(j + k) * NB + fr, -(double)a);
+    }
+    __syncthreads();                                   // shared panel blocks consumed
+    if (j + 1 < nbr) sw_prefetch(S, i, j + 1, k0, G, mbj[j + 1], false, pre);
     ++step;
-    group_barrier(cnt, step * (unsigned)G);
+    if (!(dbg & 2)) group_barrier(cnt, step * (unsigned)G);
   }
-  // ---------------- diagonal: w_j = D_j y_j ; s = 0 ----------------
+  // ---------------- diagonal: w_j = D_j y_j (FP64) ; s = 0 ----------------
+  if (nbr > 0) sw_prefetch(S, i, nbr - 1, k0, G, rlen[nbr - 1], true, pre);
   for (int j = cta; j < nbr; j += G) {
     if (tid < NB) xs[tid] = __ldcg(y + (size_t)j * NB + tid);
     __syncthreads();
@@ -367,33 +405,44 @@ k_sw_solve(GfSchwarz Sf, int G_f, int first_block, int nf, GfSchwarz Sc, int G_c
   group_barrier(cnt, step * (unsigned)G);
   // ---------------- backward: x_j = w_j - s_j ; s_{j-k} += M(j, j-k)^T x_j ----------------
   for (int j = nbr - 1; j >= 0; --j) {
-    if (tid < NB) xs[tid] = __ldcg(y + (size_t)j * NB + tid) - __ldcg(sv + (size_t)j * NB + tid);
-    __syncthreads();
-    for (int k = k0; k <= rlen[j]; k += G) {
-      const float* L = sw_block32(S, i, j - k, k) + (size_t)(w * 8) * NB;
-      float l0[8], l1[8];
-#pragma unroll
-      for (int rr = 0; rr < 8; ++rr) { l0[rr] = __ldcs(L + rr * NB + lane); l1[rr] = __ldcs(L + rr * NB + lane + 32); }
-      double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-      for (int rr = 0; rr < 8; ++rr) {
-        const double xr = xs[w * 8 + rr];
-        a0 = fma((double)l0[rr], xr, a0);
-        a1 = fma((double)l1[rr], xr, a1);
-      }
-      __syncthreads();
-      red[w][lane] = a0; red[w][lane + 32] = a1;
-      __syncthreads();
-      if (tid < NB) {
-        double v = 0.0;
-#pragma unroll
-        for (int ww = 0; ww < 8; ++ww) v += red[ww][tid];
-        double* dst = sv + (size_t)(j - k) * NB + tid;
-        __stcg(dst, __ldcg(dst) + v);
-      }
+    if (tid < NB) {
+      const double xv = __ldcg(y + (size_t)j * NB + tid) - __ldcg(sv + (size_t)j * NB + tid);
+      xs[tid] = xv; xf[tid] = (float)xv;
     }
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    float xr[16];
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(xf + bq * 16 + c);
+      xr[c] = v.x; xr[c + 1] = v.y; xr[c + 2] = v.z; xr[c + 3] = v.w;
+    }
+    int t = 0;
+    for (int k = k0; k <= rlen[j]; k += G, ++t) {
+      // block (row j, col j-k) lives in panel j-k at offset k; apply its transpose:
+      // thread (column bc, quarter bq) sums 16 rows, the four quarters are combined in smem
+      float a = 0.f;
+      if (t < PF) {
+        const float* p = pre + t * PBLK + (bq * 16) * LDS + bc;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) a = fmaf(p[r * LDS], xr[r], a);
+      } else {
+        const float* p = sw_block32(S, i, j - k, k) + (bq * 16) * NB + bc;
+        float m[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) m[r] = __ldcs(p + r * NB);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) a = fmaf(m[r], xr[r], a);
+      }
+      __syncthreads();
+      red[bq][bc] = a;
+      __syncthreads();
+      if (tid < NB) atomicAdd(sv + (size_t)(j - k) * NB + tid, (double)((red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid])));
+    }
+    __syncthreads();
+    if (j > 0) sw_prefetch(S, i, j - 1, k0, G, rlen[j - 1], true, pre);
     ++step;
-    group_barrier(cnt, step * (unsigned)G);
+    if (!(dbg & 2)) group_barrier(cnt, step * (unsigned)G);
     // everyone has read w_j and s_j: the final x_j can now replace w_j
     if (cta == 0 && tid < NB) __stcg(y + (size_t)j * NB + tid, xs[tid]);
     __syncthreads();
@@ -461,7 +510,8 @@ static int sw_caps(int* sms_out, int* occ_out) {
   if (!sms) {
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sw_solve, 256, 0);
+    cudaFuncSetAttribute(k_sw_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PF * PBLK * sizeof(float)));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sw_solve, 256, PF * PBLK * sizeof(float));
     int lim = 4;
     if (const char* ev = getenv("GF_SW_OCC")) lim = atoi(ev);
     if (occ > lim) occ = lim;
@@ -489,6 +539,9 @@ extern "C" int gf_schwarz_apply2(const GfSchwarz* Sf, const double* r_f, double*
   int sms, occ;
   const int cap = sw_caps(&sms, &occ);           // all CTAs of one launch must be co-resident
   GfSchwarz Sfv = *Sf, Scv = Sc ? *Sc : *Sf;
+  static int dbg = -1;
+  if (dbg < 0) { dbg = 0; if (const char* ev = getenv("GF_SW_DEBUG")) dbg = atoi(ev); }
+  Sfv.ctas_per_block = dbg; Scv.ctas_per_block = dbg;
   int G_c = 0;
   if (Sc) { G_c = cap / 6; if (G_c > Sc->max_mb) G_c = Sc->max_mb; if (G_c < 1) G_c = 1; }
   int G = (cap - G_c) / Sf->nblocks;
@@ -500,7 +553,7 @@ extern "C" int gf_schwarz_apply2(const GfSchwarz* Sf, const double* r_f, double*
     int first = b0;
     int gcl = (b0 == 0) ? G_c : 0;               // the coarse block rides along with the first batch
     void* args[] = {&Sfv, &G, &first, &nb_l, &Scv, &gcl};
-    e = cudaLaunchCooperativeKernel((void*)k_sw_solve, dim3(nb_l * G + gcl), dim3(256), args, 0, st);
+    e = cudaLaunchCooperativeKernel((void*)k_sw_solve, dim3(nb_l * G + gcl), dim3(256), args, PF * PBLK * sizeof(float), st);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchCooperativeKernel(k_sw_solve)");
     count_launch(1);
   }
