@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgoldfish_b200.so")
+LIB_PATH = os.environ.get("GF_LIB", os.path.join(_HERE, "libgoldfish_b200.so"))   # GF_LIB: tuning experiments only
 
 GF_OUT_R, GF_OUT_K, GF_OUT_W, GF_OUT_P, GF_OUT_T = 1, 2, 4, 8, 16
 GF_ERRORS = {1: "bad argument", 2: "CUDA error", 3: "not converged", 4: "breakdown", 5: "NaN"}

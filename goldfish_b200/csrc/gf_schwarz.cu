@@ -64,20 +64,20 @@ k_sw_fill(GfSchwarz S, GfCsr K) {
 
 // ---- in-shared-memory Cholesky of a 64 x 64 block (lower), all 256 threads ------
 __device__ __forceinline__ void chol64(double (*A)[NB + 1], int32_t* flag) {
-  const int tid = threadIdx.x;
+  // right-looking, 256 threads: thread (r = tid/4, q = tid%4) owns row r, columns 16q..16q+15
+  const int tid = threadIdx.x, r = tid >> 2, q = tid & 3;
   for (int c = 0; c < NB; ++c) {
     if (tid == 0) {
       const double d = A[c][c];
       if (!(d > 0.0)) { atomicExch(flag, 1); A[c][c] = 1.0; } else A[c][c] = sqrt(d);
     }
     __syncthreads();
-    const double inv = 1.0 / A[c][c];
-    if (tid > c && tid < NB) A[tid][c] *= inv;
+    if (q == 0 && r > c) A[r][c] *= 1.0 / A[c][c];
     __syncthreads();
-    const int m = NB - c - 1;
-    for (int e = tid; e < m * m; e += 256) {
-      const int r = c + 1 + e / m, cc = c + 1 + e % m;
-      if (cc <= r) A[r][cc] -= A[r][c] * A[cc][c];
+    if (r > c) {
+      const double lrc = A[r][c];
+      const int lo = max(c + 1, 16 * q), hi = min(r, 16 * q + 15);
+      for (int cc = lo; cc <= hi; ++cc) A[r][cc] = fma(-lrc, A[cc][c], A[r][cc]);
     }
     __syncthreads();
   }
@@ -293,7 +293,10 @@ __device__ __forceinline__ const float* sw_block32(const GfSchwarz& S, int i, in
   return S.band32 + S.off_col[S.off_j[i] + j] + (size_t)k * NB2;
 }
 
-constexpr int PF = 4;        // panel blocks of the NEXT step prefetched into shared memory per CTA
+#ifndef GF_PF
+#define GF_PF 4
+#endif
+constexpr int PF = GF_PF;   // panel blocks of the NEXT step prefetched into shared memory per CTA
 constexpr int LDS = NB + 4;  // padded row stride (floats) of a prefetched block: 16-B aligned, conflict-light
 constexpr int PBLK = NB * LDS;
 

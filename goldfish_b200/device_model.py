@@ -170,7 +170,10 @@ class DeviceModel:
         self.schwarz_sub = schwarz_sub
         max_ne = max(max(P.neu, P.nev) for P in S.patches)
         if coarse_nc == "auto":
-            coarse_nc = 0 if max_ne < 16 else int(min(24, max(8, max_ne // 8)))
+            # the coarse sweeps run beside the fine ones: keep their chain shorter than the fine chains
+            # (which shrink per GPU when the blocks are spread over several ranks)
+            cap_nc = 24 if self.world < 4 else 16
+            coarse_nc = 0 if max_ne < 16 else int(min(cap_nc, max(8, max_ne // 8)))
         self.coarse_nc = int(coarse_nc) if precond == "schwarz" else 0
         self.problem = problem
         self._pc = None

@@ -8,7 +8,7 @@ from goldfish_b200.device_model import DeviceModel, _ptr
 
 n_el = int(sys.argv[1]) if len(sys.argv) > 1 else 201
 pr, kw = bench.workload(n_el)
-dm = DeviceModel(pr, **kw)
+dm = DeviceModel(pr, coarse_nc=(int(os.environ["NC"]) if "NC" in os.environ else "auto"), **kw)
 dm.u.zero_(); dm.assemble(residual=True, tangent=True)
 dm.factor_preconditioner()
 pc = dm._precond_struct(); st = dm._stream(); lib = dm.lib
@@ -35,4 +35,5 @@ print("axpby                 %.3f ms" % T(lambda: dm.axpby(1.0, x, 1.0, y)))
 its0 = 0
 import time
 torch.cuda.synchronize(); t0 = time.time(); dm.solve(r.clone()); torch.cuda.synchronize(); t1 = time.time()
+tf0 = time.time(); dm.factor_preconditioner(); torch.cuda.synchronize(); print("refactor %.1f ms" % ((time.time() - tf0) * 1e3))
 print("full solve %.1f ms, its %d -> %.3f ms/it" % ((t1 - t0) * 1e3, dm.last_krylov_its, (t1 - t0) * 1e3 / dm.last_krylov_its))
