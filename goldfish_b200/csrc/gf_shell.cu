@@ -718,22 +718,369 @@ static int launch_k2(const GfModel* m, int what, const GfShellOut* out, cudaStre
   count_launch(-1);
   return check_launch("k_shell_k2");
 }
+
+// ---------------------------------------------------------------------------------
+// Shape / thickness passes, version 2: two quadrature points per warp pass, same lane
+// layout as k_shell_k2.  PT = 1: dR/dCP_f, dW/dCP_f, dV/dCP_f (lane & 15 = g_X direction);
+// PT = 2: dR/dt, dW/dt, dV/dt, dW/du (the single t direction, reference part in plain doubles).
+// ---------------------------------------------------------------------------------
+struct WarpSmemP2 {
+  double Xc[16][4];
+  double uc[16][3];
+  double Phi[2][6][16];
+  double g[2][32];
+  double Gv[2][16];      // grad values; [15] = J
+  double Ht[2][16];      // d grad / d t ; [15] = d e / d t
+  double Ed[2][16];
+  double Jd[2][16];
+  double Hc[2][15][17];  // Hc[h][m][dx] = d grad_m / d gX_dx
+  double G[15][48];
+  double tw[2][16];
+  double the[16];
+  int ninfo[16][8];
+  int tdof[16];
+};
+
+template <int PT>
+__global__ void __launch_bounds__(128)
+k_shell_p2(GfModel M, GfShellOut O, int color_begin, int color_count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpSmemP2& S = reinterpret_cast<WarpSmemP2*>(smem_raw)[warp];
+  const int slot = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (slot >= color_count) return;
+  const int el = M.color_elem[color_begin + slot];
+  const GfPatchDesc P = M.patches[M.elem_patch[el]];
+  const int eu = M.elem_eu[el], ev = M.elem_ev[el];
+  const int su = P.span_u_off + eu, sv = P.span_v_off + ev;
+  const int I0 = M.first_cp_u[su], J0 = M.first_cp_v[sv];
+  const int ncp = P.n_u * P.n_v;
+  const double area = M.span_h_u[su] * M.span_h_v[sv];
+  const int nq = M.nq;
+  const int half = lane >> 4, an = lane & 15;
+
+  if (lane < 16) {
+    const int lu = lane & 3, lv = lane >> 2;
+    const int I = I0 + lu, J = J0 + lv;
+    const int cpl = I + J * P.n_u;
+    const double4 c = reinterpret_cast<const double4*>(M.cp)[P.cp_off + cpl];
+    S.Xc[lane][0] = c.x; S.Xc[lane][1] = c.y; S.Xc[lane][2] = c.z; S.Xc[lane][3] = c.w;
+    const double* up = M.u + P.dof_off + cpl;
+    S.uc[lane][0] = up[0]; S.uc[lane][1] = up[ncp]; S.uc[lane][2] = up[2 * (size_t)ncp];
+    const int Ilo = M.cp_lo_u[P.cpd_u_off + I], Ihi = M.cp_hi_u[P.cpd_u_off + I];
+    const int Jlo = M.cp_lo_v[P.cpd_v_off + J], Jhi = M.cp_hi_v[P.cpd_v_off + J];
+    S.ninfo[lane][0] = cpl; S.ninfo[lane][1] = I; S.ninfo[lane][2] = J;
+    S.ninfo[lane][3] = Ilo; S.ninfo[lane][4] = Ihi - Ilo + 1; S.ninfo[lane][5] = Jlo;
+    S.ninfo[lane][6] = (Ihi - Ilo + 1) * (Jhi - Jlo + 1);
+    S.ninfo[lane][7] = M.row_nlow[P.cp_off + cpl];
+  }
+  int nt = 1;
+  if (P.th_kind == GF_TH_LINEAR) nt = 4; else if (P.th_kind == GF_TH_IGA) nt = 16;
+  if (lane < nt) {
+    int td;
+    if (P.th_kind == GF_TH_CONST) td = 0;
+    else if (P.th_kind == GF_TH_LINEAR) td = (eu + (lane & 1)) + (ev + (lane >> 1)) * (P.neu + 1);
+    else td = (I0 + (lane & 3)) + (J0 + (lane >> 2)) * P.n_u;
+    S.tdof[lane] = td;
+    S.the[lane] = M.theta[P.th_off + td];
+  }
+  __syncwarp();
+
+  constexpr int NACC = (PT == 2) ? 24 : 72;
+  double acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+  double racc0 = 0.0, racc1 = 0.0, vacc0 = 0.0, vacc1 = 0.0;
+  const int ag = lane >> 3, bg = lane & 7;
+  const int mh = (nt + 1) >> 1, m0 = half * mh;
+  const double* tu = M.tab_u + (size_t)su * nq * 12;
+  const double* tv = M.tab_v + (size_t)sv * nq * 12;
+
+  for (int q0 = 0; q0 < nq; q0 += 2) {
+    const bool valid = (q0 + half) < nq;
+    const int q = valid ? q0 + half : q0;
+    {
+      const int lu = an & 3, lv = an >> 2;
+      const double* a = tu + q * 12;
+      const double* b = tv + q * 12;
+      const double u0 = a[lu], u1 = a[4 + lu], u2 = a[8 + lu];
+      const double v0 = b[lv], v1 = b[4 + lv], v2 = b[8 + lv];
+      double N = u0 * v0, Nu = u1 * v0, Nv = u0 * v1, Nuu = u2 * v0, Nvv = u0 * v2, Nuv = u1 * v1;
+      const double nraw = N;
+      if (P.rational) {
+        const double w = S.Xc[an][3];
+        double W = N * w, Wu = Nu * w, Wv = Nv * w, Wuu = Nuu * w, Wvv = Nvv * w, Wuv = Nuv * w;
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) {
+          W += __shfl_xor_sync(0xffffffffu, W, o);
+          Wu += __shfl_xor_sync(0xffffffffu, Wu, o);
+          Wv += __shfl_xor_sync(0xffffffffu, Wv, o);
+          Wuu += __shfl_xor_sync(0xffffffffu, Wuu, o);
+          Wvv += __shfl_xor_sync(0xffffffffu, Wvv, o);
+          Wuv += __shfl_xor_sync(0xffffffffu, Wuv, o);
+        }
+        const double iW = 1.0 / W;
+        const double f = N * iW;
+        const double fu = (Nu - f * Wu) * iW;
+        const double fv = (Nv - f * Wv) * iW;
+        const double fuu = (Nuu - 2.0 * fu * Wu - f * Wuu) * iW;
+        const double fvv = (Nvv - 2.0 * fv * Wv - f * Wvv) * iW;
+        const double fuv = (Nuv - fu * Wv - fv * Wu - f * Wuv) * iW;
+        N = f; Nu = fu; Nv = fv; Nuu = fuu; Nvv = fvv; Nuv = fuv;
+      }
+      S.Phi[half][0][an] = N; S.Phi[half][1][an] = Nu; S.Phi[half][2][an] = Nv;
+      S.Phi[half][3][an] = Nuu; S.Phi[half][4][an] = Nvv; S.Phi[half][5][an] = Nuv;
+      if (P.th_kind == GF_TH_IGA) S.tw[half][an] = nraw;
+      else if (P.th_kind == GF_TH_LINEAR) { if (an < 4) S.tw[half][an] = M.tw_lin[q * 4 + an]; }
+      else if (an == 0) S.tw[half][0] = 1.0;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double val = 0.0;
+      if (lane < 15) {
+        const int k = lane / 3 + 1, c = lane % 3;
+#pragma unroll
+        for (int a = 0; a < 16; ++a) val = fma(S.Phi[h][k][a], S.Xc[a][c], val);
+      } else if (lane == 15) {
+        for (int m = 0; m < nt; ++m) val = fma(S.tw[h][m], S.the[m], val);
+      } else if (lane < 31) {
+        const int k = (lane - 16) / 3 + 1, c = (lane - 16) % 3;
+#pragma unroll
+        for (int a = 0; a < 16; ++a) val = fma(S.Phi[h][k][a], S.uc[a][c], val);
+      }
+      S.g[h][lane] = val;
+    }
+    __syncwarp();
+    if (PT == 1) {
+      // lane (half, d): derivative along g_X[d] at fixed u_hom (x = X + u moves with X)
+      Dual gX[15], gu[15], grad[15], e, J;
+#pragma unroll
+      for (int k = 0; k < 15; ++k) {
+        gX[k] = Dual(S.g[half][k], (an == k) ? 1.0 : 0.0);
+        gu[k] = Dual(S.g[half][16 + k]);
+      }
+      kl_shell_point<Dual>(gX, gu, Dual(S.g[half][15]), P.E, P.nu, e, J, grad);
+      if (an < 15) {
+#pragma unroll
+        for (int m = 0; m < 15; ++m) S.Hc[half][m][an] = grad[m].d;
+        S.Ed[half][an] = e.d; S.Jd[half][an] = J.d;
+      }
+    } else {
+      double gXd[15];
+      Dual gu[15], grad[15], e;
+#pragma unroll
+      for (int k = 0; k < 15; ++k) { gXd[k] = S.g[half][k]; gu[k] = Dual(S.g[half][16 + k]); }
+      KlRef<double> R;
+      kl_reference<double>(gXd, P.E, P.nu, R);
+      kl_shell_point_fixed_ref<Dual>(gXd, R, gu, Dual(S.g[half][15], 1.0), e, grad);
+      if (an == 0) {
+#pragma unroll
+        for (int m = 0; m < 15; ++m) { S.Gv[half][m] = grad[m].v; S.Ht[half][m] = grad[m].d; }
+        S.Gv[half][15] = R.J; S.Ht[half][15] = e.d;
+      }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      if (q0 + h >= nq) break;
+      const double wq = M.qw[q0 + h] * area;
+      const double tq = S.g[h][15];
+      if (PT == 1) {
+        for (int o = lane; o < 720; o += 32) {
+          const int m = o / 48, fb = o - m * 48;
+          const int f = fb >> 4, b = fb & 15;
+          double s = 0.0;
+#pragma unroll
+          for (int l = 0; l < 5; ++l) s = fma(S.Hc[h][m][l * 3 + f], S.Phi[h][1 + l][b], s);
+          S.G[m][fb] = wq * s;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          double ph[4];
+#pragma unroll
+          for (int aa = 0; aa < 4; ++aa) ph[aa] = S.Phi[h][1 + k][4 * ag + aa];
+#pragma unroll
+          for (int f = 0; f < 3; ++f)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const double g0 = S.G[3 * k + i][16 * f + 2 * bg], g1 = S.G[3 * k + i][16 * f + 2 * bg + 1];
+#pragma unroll
+              for (int aa = 0; aa < 4; ++aa) {
+                acc[((f * 3 + i) * 4 + aa) * 2 + 0] = fma(ph[aa], g0, acc[((f * 3 + i) * 4 + aa) * 2 + 0]);
+                acc[((f * 3 + i) * 4 + aa) * 2 + 1] = fma(ph[aa], g1, acc[((f * 3 + i) * 4 + aa) * 2 + 1]);
+              }
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+          double dj[2];
+#pragma unroll
+          for (int bb = 0; bb < 2; ++bb)
+            dj[bb] = wq * (S.Jd[h][f] * S.Phi[h][1][2 * bg + bb] + S.Jd[h][3 + f] * S.Phi[h][2][2 * bg + bb]);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int aa = 0; aa < 4; ++aa) {
+              const double c = -P.f[i] * S.Phi[h][0][4 * ag + aa];
+              acc[((f * 3 + i) * 4 + aa) * 2 + 0] = fma(c, dj[0], acc[((f * 3 + i) * 4 + aa) * 2 + 0]);
+              acc[((f * 3 + i) * 4 + aa) * 2 + 1] = fma(c, dj[1], acc[((f * 3 + i) * 4 + aa) * 2 + 1]);
+            }
+        }
+        {
+          const int f0 = half ? 2 : 0;
+          double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+#pragma unroll
+          for (int l = 0; l < 5; ++l) {
+            s0 = fma(S.Ed[h][3 * l + f0], S.Phi[h][1 + l][an], s0);
+            s1 = fma(S.Ed[h][3 * l + 1], S.Phi[h][1 + l][an], s1);
+          }
+#pragma unroll
+          for (int l = 0; l < 2; ++l) {
+            t0 = fma(S.Jd[h][3 * l + f0], S.Phi[h][1 + l][an], t0);
+            t1 = fma(S.Jd[h][3 * l + 1], S.Phi[h][1 + l][an], t1);
+          }
+          racc0 += wq * s0; racc1 += wq * s1;
+          vacc0 += wq * tq * t0; vacc1 += wq * tq * t1;
+        }
+      } else {
+        double r[3], du[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          double s = 0.0, s2 = 0.0;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            s = fma(S.Phi[h][1 + k][an], S.Ht[h][3 * k + i], s);
+            s2 = fma(S.Phi[h][1 + k][an], S.Gv[h][3 * k + i], s2);
+          }
+          r[i] = wq * s; du[i] = wq * s2;
+        }
+#pragma unroll
+        for (int mm = 0; mm < 8; ++mm) {
+          const int m = m0 + mm;
+          const double t = (mm < mh && m < nt) ? S.tw[h][m] : 0.0;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) acc[i * 8 + mm] = fma(r[i], t, acc[i * 8 + mm]);
+        }
+        racc0 += half ? du[2] : du[0];
+        racc1 += du[1];
+        if (lane < nt) {
+          vacc0 += wq * S.Ht[h][15] * S.tw[h][lane];
+          vacc1 += wq * S.Gv[h][15] * S.tw[h][lane];
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  const size_t dof0 = (size_t)P.dof_off;
+  if (PT == 1) {
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      if (P.pcol_off[f] < 0 || M.P[f].vals == nullptr) continue;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int aa = 0; aa < 4; ++aa) {
+          const int a = 4 * ag + aa;
+          const int* na = S.ninfo[a];
+          const size_t row = dof0 + (size_t)i * ncp + na[0];
+          if (M.bc[row]) continue;
+          const int64_t base = M.P[f].indptr[row];
+#pragma unroll
+          for (int bb = 0; bb < 2; ++bb) {
+            const int* nb = S.ninfo[2 * bg + bb];
+            const int64_t pos = base + (nb[2] - na[5]) * na[4] + (nb[1] - na[3]);
+            M.P[f].vals[pos] += acc[((f * 3 + i) * 4 + aa) * 2 + bb];
+          }
+        }
+    }
+    const int cpl = S.ninfo[an][0];
+    const int f0 = half ? 2 : 0;
+    if (P.pcol_off[f0] >= 0 && O.dWdP[f0]) {
+      O.dWdP[f0][P.pcol_off[f0] + cpl] += racc0;
+      if (O.dVdP[f0]) O.dVdP[f0][P.pcol_off[f0] + cpl] += vacc0;
+    }
+    if (half == 0 && P.pcol_off[1] >= 0 && O.dWdP[1]) {
+      O.dWdP[1][P.pcol_off[1] + cpl] += racc1;
+      if (O.dVdP[1]) O.dVdP[1][P.pcol_off[1] + cpl] += vacc1;
+    }
+  } else {
+    if (M.T.vals != nullptr) {
+      const int* na = S.ninfo[an];
+      int lo_u = 0, wu = 1, lo_v = 0;
+      if (P.th_kind == GF_TH_LINEAR) {
+        lo_u = M.el_lo_u[P.cpd_u_off + na[1]];
+        wu = M.el_hi_u[P.cpd_u_off + na[1]] - lo_u + 2;
+        lo_v = M.el_lo_v[P.cpd_v_off + na[2]];
+      } else if (P.th_kind == GF_TH_IGA) {
+        lo_u = na[3]; wu = na[4]; lo_v = na[5];
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const size_t row = dof0 + (size_t)i * ncp + na[0];
+        const int64_t base = M.T.indptr[row];
+#pragma unroll
+        for (int mm = 0; mm < 8; ++mm) {
+          const int m = m0 + mm;
+          if (!(mm < mh && m < nt)) continue;
+          int64_t pos = base;
+          if (P.th_kind == GF_TH_LINEAR) {
+            const int vI = eu + (m & 1), vJ = ev + (m >> 1);
+            pos += (vJ - lo_v) * wu + (vI - lo_u);
+          } else if (P.th_kind == GF_TH_IGA) {
+            const int* nb = S.ninfo[m];
+            pos += (nb[2] - lo_v) * wu + (nb[1] - lo_u);
+          }
+          M.T.vals[pos] += acc[i * 8 + mm];
+        }
+      }
+    }
+    if (O.dWdu) {
+      const int cpl = S.ninfo[an][0];
+      if (half == 0) { O.dWdu[dof0 + cpl] += racc0; O.dWdu[dof0 + ncp + cpl] += racc1; }
+      else O.dWdu[dof0 + 2 * (size_t)ncp + cpl] += racc0;
+    }
+    if (P.th_kind == GF_TH_CONST) {
+      if (lane == 0 && O.dt_el) { O.dt_el[2 * (size_t)el] = vacc0; O.dt_el[2 * (size_t)el + 1] = vacc1; }
+    } else if (lane < nt) {
+      if (O.dWdt) O.dWdt[P.th_off + S.tdof[lane]] += vacc0;
+      if (O.dVdt) O.dVdt[P.th_off + S.tdof[lane]] += vacc1;
+    }
+  }
+}
+
+template <int PT>
+static int launch_p2(const GfModel* m, const GfShellOut* out, cudaStream_t st) {
+  const size_t smem = 4 * sizeof(WarpSmemP2);
+  cudaError_t e = cudaFuncSetAttribute(k_shell_p2<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(k_shell_p2)");
+  for (int c = 0; c < m->num_colors; ++c) {
+    const int b = m->color_ptr_h[c], n = m->color_ptr_h[c + 1] - b;
+    if (n <= 0) continue;
+    k_shell_p2<PT><<<(n + 3) / 4, 128, smem, st>>>(*m, *out, b, n);
+    count_launch(1);
+  }
+  count_launch(-1);
+  return check_launch("k_shell_p2");
+}
 }  // namespace gf
 
 extern "C" int gf_shell_assemble(const GfModel* m, int what, const GfShellOut* out, void* stream) {
   if (!m || !out) return gf::set_error(GF_ERR_BADARG, "gf_shell_assemble: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = GF_OK;
+  static const bool v1 = getenv("GF_SHELL_V1") != nullptr;   // keep the one-point-per-pass kernels reachable
   if (what & (GF_OUT_R | GF_OUT_K | GF_OUT_W)) {
     if ((what & GF_OUT_R) && !out->R) return gf::set_error(GF_ERR_BADARG, "GF_OUT_R without out->R");
     if ((what & GF_OUT_W) && !out->WV) return gf::set_error(GF_ERR_BADARG, "GF_OUT_W without out->WV");
-    static const bool v1 = getenv("GF_SHELL_V1") != nullptr;   // keep the one-point-per-pass kernel reachable
     rc = v1 ? gf::launch_mode<gf::MODE_K>(m, what, out, st) : gf::launch_k2(m, what, out, st);
     if (rc) return rc;
   }
-  if (what & GF_OUT_P) { rc = gf::launch_mode<gf::MODE_P>(m, what, out, st); if (rc) return rc; }
+  if (what & GF_OUT_P) { rc = v1 ? gf::launch_mode<gf::MODE_P>(m, what, out, st) : gf::launch_p2<1>(m, out, st); if (rc) return rc; }
   if (what & GF_OUT_T) {
-    rc = gf::launch_mode<gf::MODE_T>(m, what, out, st);
+    rc = v1 ? gf::launch_mode<gf::MODE_T>(m, what, out, st) : gf::launch_p2<2>(m, out, st);
     if (rc) return rc;
     if (out->dt_el && (out->dWdt || out->dVdt)) {
       gf::k_reduce_dt<<<m->num_patches, 256, 0, st>>>(*m, *out);
