@@ -83,69 +83,66 @@ __device__ __forceinline__ void chol64(double (*A)[NB + 1], int32_t* flag) {
   }
 }
 
-// ---- panel step j: every CTA factors the diagonal block itself (redundantly, it
-// is tiny) and CTA k >= 1 solves its block  B_k <- B_k L_jj^-T  by substitution.
-// One launch per step instead of potrf -> trsm.
+// ---- diagonal block of step j: Cholesky and the inverse of the factor, one CTA per block ----
 __global__ void __launch_bounds__(256)
-k_sw_panel(GfSchwarz S, int j) {
-  const int i = blockIdx.y, k = blockIdx.x;
-  if (j >= S.nbr[i] || k > sw_mb(S, i, j)) return;
-  extern __shared__ double sm[];
-  double (*A)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
-  double (*B)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm + NB * (NB + 1));
-  double* dblk = sw_block(S, i, j, 0);
-  const int tid = threadIdx.x;
-  for (int e = tid; e < NB2; e += 256) A[e / NB][e % NB] = dblk[e];
-  double* blk = sw_block(S, i, j, k);
-  if (k > 0) for (int e = tid; e < NB2; e += 256) B[e / NB][e % NB] = blk[e];
-  __syncthreads();
-  chol64(A, S.flag);
-  if (k == 0) {
-    // L_jj goes to the invd slot (inverted in place later); the band keeps A_jj so that
-    // the other CTAs of this launch, which may start later, still read the unfactored block
-    double* Lout = S.invd + S.off_inv[i] + (size_t)j * NB2;
-    for (int e = tid; e < NB2; e += 256) { const int r = e / NB, c = e % NB; Lout[e] = (c <= r) ? A[r][c] : 0.0; }
-    return;
-  }
-  // X L^T = B  =>  X[r][c] = (B[r][c] - sum_{m<c} X[r][m] L[c][m]) / L[c][c]; 4 threads per row
-  const int r = tid >> 2, q = tid & 3;
-  for (int c = 0; c < NB; ++c) {
-    double sdot = 0.0;
-    for (int m = q; m < c; m += 4) sdot = fma(B[r][m], A[c][m], sdot);
-    sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
-    sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-    if (q == 0) B[r][c] = (B[r][c] - sdot) / A[c][c];
-    __syncwarp();
-  }
-  __syncthreads();
-  for (int e = tid; e < NB2; e += 256) blk[e] = B[e / NB][e % NB];
-}
-
-// ---- inverse of every diagonal factor block (off the critical path) -----------
-__global__ void __launch_bounds__(256)
-k_sw_invert(GfSchwarz S) {
-  const int i = blockIdx.y, j = blockIdx.x;
+k_sw_potrf(GfSchwarz S, int j) {
+  const int i = blockIdx.x;
   if (j >= S.nbr[i]) return;
   extern __shared__ double sm[];
   double (*A)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
   double (*Li)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm + NB * (NB + 1));
-  double* inv = S.invd + S.off_inv[i] + (size_t)j * NB2;     // holds L_jj on entry
+  const double* dblk = sw_block(S, i, j, 0);
   const int tid = threadIdx.x;
-  for (int e = tid; e < NB2; e += 256) { A[e / NB][e % NB] = inv[e]; Li[e / NB][e % NB] = 0.0; }
+  for (int e = tid; e < NB2; e += 256) A[e / NB][e % NB] = dblk[e];
   __syncthreads();
-  if (tid < NB) {          // thread t solves L x = e_t
-    const int t = tid;
-    Li[t][t] = 1.0 / A[t][t];
-    for (int r = t + 1; r < NB; ++r) {
-      double s0 = 0.0, s1 = 0.0;
-      int m = t;
-      for (; m + 1 < r; m += 2) { s0 = fma(A[r][m], Li[m][t], s0); s1 = fma(A[r][m + 1], Li[m + 1][t], s1); }
-      if (m < r) s0 = fma(A[r][m], Li[m][t], s0);
-      Li[r][t] = -(s0 + s1) / A[r][r];
+  chol64(A, S.flag);
+  // inverse of L: column t by 4 threads (t = tid/4), rows sequential, dot products split 4 ways
+  {
+    const int t = tid >> 2, q = tid & 3;
+    if (q == 0) Li[t][t] = 1.0 / A[t][t];
+    __syncwarp();
+    for (int r = 1; r < NB; ++r) {          // uniform trip count: the shuffles need the whole warp
+      double sdot = 0.0;
+      if (r > t) for (int m = t + q; m < r; m += 4) sdot = fma(A[r][m], Li[m][t], sdot);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+      if (q == 0 && r > t) Li[r][t] = -sdot / A[r][r];
+      __syncwarp();
     }
   }
   __syncthreads();
+  double* inv = S.invd + S.off_inv[i] + (size_t)j * NB2;
   for (int e = tid; e < NB2; e += 256) { const int r = e / NB, c = e % NB; inv[e] = (c <= r) ? Li[r][c] : 0.0; }
+}
+
+// ---- panel of step j: B_k <- B_k L_jj^-T as a 64^3 product with the inverted factor ----
+__global__ void __launch_bounds__(256)
+k_sw_trsm(GfSchwarz S, int j) {
+  const int i = blockIdx.y, k = blockIdx.x + 1;
+  if (j >= S.nbr[i] || k > sw_mb(S, i, j)) return;
+  extern __shared__ double sm[];
+  double (*B)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
+  double (*Li)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm + NB * (NB + 1));
+  double* blk = sw_block(S, i, j, k);
+  const double* inv = S.invd + S.off_inv[i] + (size_t)j * NB2;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB2; e += 256) { B[e / NB][e % NB] = blk[e]; Li[e / NB][e % NB] = inv[e]; }
+  __syncthreads();
+  const int r0 = (tid / 16) * 4, c0 = (tid % 16) * 4;   // out[r][c] = sum_{m<=c} B[r][m] Linv[c][m]
+  double acc[4][4] = {};
+  for (int m = 0; m < NB; ++m) {
+    double a[4], b[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) { a[x] = B[r0 + x][m]; b[x] = Li[c0 + x][m]; }
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) blk[(r0 + x) * NB + c0 + y] = acc[x][y];
 }
 
 // ---- trailing update: A(j+k1, j+k2) -= B_k1 B_k2^T ------------------------------
@@ -483,19 +480,21 @@ extern "C" int gf_schwarz_factor(const GfSchwarz* S, const GfCsr* K, void* strea
   k_sw_fill<<<gf, 256, 0, st>>>(*S, *K);
   const size_t smem = 2 * NB * (NB + 1) * sizeof(double);
   e = cudaFuncSetAttribute(k_sw_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_potrf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(k_sw_*)");
   for (int j = 0; j < S->max_nbr; ++j) {
     const int m = S->step_mb_h[j];      // tallest panel of this step over all patch blocks
-    k_sw_panel<<<dim3(m + 1, S->nblocks), 256, smem, st>>>(*S, j);
-    if (m > 0) k_sw_update<<<dim3(m * (m + 1) / 2, S->nblocks), 256, smem, st>>>(*S, j);
-    count_launch(2);
+    k_sw_potrf<<<S->nblocks, 256, smem, st>>>(*S, j);
+    if (m > 0) {
+      k_sw_trsm<<<dim3(m, S->nblocks), 256, smem, st>>>(*S, j);
+      k_sw_update<<<dim3(m * (m + 1) / 2, S->nblocks), 256, smem, st>>>(*S, j);
+    }
+    count_launch(3);
   }
   e = cudaFuncSetAttribute(k_sw_convert_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sw_convert_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(k_sw_convert)");
-  k_sw_invert<<<dim3(S->max_nbr, S->nblocks), 256, smem, st>>>(*S);
   if (S->max_mb > 0) k_sw_convert_panel<<<dim3(S->max_mb, S->max_nbr, S->nblocks), 256, smem, st>>>(*S);
   k_sw_convert_diag<<<dim3(S->max_nbr, S->nblocks), 256, smem, st>>>(*S);
   k_sw_to_f32<<<2048, 256, 0, st>>>(S->band, S->band32, S->band_len);
