@@ -245,12 +245,13 @@ def main():
     import torch
     import torch.distributed as dist
     import __graft_entry__ as g
-    if rank == 0:
-        g.build()
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist.barrier()
+    if rank == 0:
+        g.build()                       # no-op when the in-tree .so is up to date
+    if world > 1:
+        dist.barrier()                  # nobody loads the library before rank 0 has (re)built it
     from goldfish_b200 import _capi as capi
     from goldfish_b200.device_model import DeviceModel
     lib = capi.load()

@@ -71,7 +71,7 @@ class GfCsrT(C.Structure):
 
 class GfSchwarz(C.Structure):
     _fields_ = [("nblocks", c_i32), ("nb", c_i32), ("max_nbr", c_i32), ("max_mb", c_i32), ("max_n_pad", c_i32),
-                ("ctas_per_block", c_i32), ("n_y", c_i64), ("band_len", c_i64),
+                ("debug_flags", c_i32), ("n_y", c_i64), ("band_len", c_i64),
                 ("n_pad", c_vp), ("nbr", c_vp), ("off_j", c_vp), ("mbj", c_vp), ("rlen", c_vp), ("off_col", c_vp),
                 ("step_mb_h", c_vp), ("off_y", c_vp), ("off_inv", c_vp),
                 ("glob", c_vp), ("gs", c_vp), ("ls", c_vp), ("off_g", c_vp), ("zptr", c_vp), ("zsrc", c_vp),

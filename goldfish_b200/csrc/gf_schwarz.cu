@@ -339,7 +339,7 @@ k_sw_solve(GfSchwarz Sf, int G_f, int first_block, int nf, GfSchwarz Sc, int G_c
   unsigned* cnt = S.barrier + i;
   unsigned step = 0;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int dbg = S.ctas_per_block;               // timing experiments only: 1 = skip GEMVs, 2 = skip barriers
+  const int dbg = S.debug_flags;               // timing experiments only: 1 = skip GEMVs, 2 = skip barriers
   const int k0 = (dbg & 1) ? 1000000 : 1 + cta;
   const int fr = tid >> 2, fq = tid & 3;           // forward: row fr, quarter fq (16 columns)
   const int bc = tid & 63, bq = tid >> 6;          // backward: column bc, quarter bq (16 rows)
@@ -543,7 +543,7 @@ extern "C" int gf_schwarz_apply2(const GfSchwarz* Sf, const double* r_f, double*
   GfSchwarz Sfv = *Sf, Scv = Sc ? *Sc : *Sf;
   static int dbg = -1;
   if (dbg < 0) { dbg = 0; if (const char* ev = getenv("GF_SW_DEBUG")) dbg = atoi(ev); }
-  Sfv.ctas_per_block = dbg; Scv.ctas_per_block = dbg;
+  Sfv.debug_flags = dbg; Scv.debug_flags = dbg;
   int G_c = 0;
   if (Sc) { G_c = cap / 6; if (G_c > Sc->max_mb) G_c = Sc->max_mb; if (G_c < 1) G_c = 1; }
   int G = (cap - G_c) / Sf->nblocks;

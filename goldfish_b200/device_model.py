@@ -459,7 +459,7 @@ class DeviceModel:
             s = capi.GfSchwarz()
             s.nblocks, s.nb = A["nblocks"], NB
             s.max_nbr, s.max_mb, s.max_n_pad = A["max_nbr"], A["max_mb"], A["max_n_pad"]
-            s.ctas_per_block = 0          # chosen in gf_schwarz_apply from the SM count and panel height
+            s.debug_flags = 0
             s.n_y, s.band_len = A["n_y"], A["band_len"]
             for k in ("n_pad", "nbr", "off_j", "mbj", "rlen", "off_col", "off_y", "off_inv", "glob", "gs", "ls", "off_g", "zptr", "zsrc",
                       "band", "band32", "invd", "y", "s", "barrier", "flag"):

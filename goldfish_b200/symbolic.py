@@ -424,9 +424,14 @@ class Symbolic:
         pen["nK"] = len(uk)
         pen["K_dest_patch"] = pr.astype(np.int32)
         # ---- dR/dCP_f penalty part ----
-        self.penP = []
+        # the gather structure depends on the patch list only: build it once per distinct list
+        self.penP, cache = [], {}
         for fi, field in enumerate(self.opt_field):
-            self.penP.append(self._penalty_P(field, nodes))
+            key = tuple(self.shopt_surf_inds[fi])
+            if key not in cache:
+                cache[key] = self._penalty_P(field, nodes)
+            pp = dict(cache[key]); pp["field"] = field
+            self.penP.append(pp)
 
     def _penalty_P(self, field, nodes):
         pen = self.pen

@@ -181,7 +181,8 @@ int gf_spmv_t(const GfCsr* A, const GfCsrT* At, const double* x, double* y, doub
  * builds the block orderings; all arrays are device pointers except *_h. */
 typedef struct GfSchwarz {
   int32_t nblocks, nb;            /* nb = 64                                          */
-  int32_t max_nbr, max_mb, max_n_pad, ctas_per_block;
+  int32_t max_nbr, max_mb, max_n_pad;
+  int32_t debug_flags;            /* 0 in production; timing experiments: 1 skip block GEMVs, 2 skip barriers */
   int64_t n_y, band_len;          /* total padded local dofs; band storage length     */
   const int32_t* n_pad;           /* [nblocks] padded local size (multiple of nb)     */
   const int32_t* nbr;             /* [nblocks] block rows                             */
