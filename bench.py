@@ -186,6 +186,27 @@ def build_facade(pr, kw):
     return nm, (DispImOpeartion(nm), IntEnergyExOperation(nm), VolumeExOperation(nm))
 
 
+def small_configs(torch):
+    """BASELINE configs[0] (plate thickness opt, C1) and configs[1] (T-beam shape opt, C2): the
+    same analysis+adjoint step at the reference's own (tiny, latency-bound) sizes."""
+    from goldfish_b200 import problems
+    from goldfish_b200.device_model import DeviceModel
+    out = {}
+    cases = {"C1_plate_thickness_N1449": (problems.plate(os.path.join(ROOT, "tests", "golden", "plate_c1_input.npz")), {}),
+             "C2_tbeam_shape_N648": (problems.tbeam(num_el=10), dict(opt_field=[0], shopt_surf_inds=[[0, 1]]))}
+    for name, (pr, kw) in cases.items():
+        st = Step(DeviceModel(pr, **kw))
+        for _ in range(2):
+            st()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            st()
+        b.record(); torch.cuda.synchronize()
+        out[name] = {"ms_per_step": a.elapsed_time(b) / 5, "newton_its": st.info["newton_its"], "krylov_its": st.info["krylov_its"]}
+    return out
+
+
 def time_kernel(torch, fn, reps, flush):
     """Average CUDA-event time of `fn` (ms) with an L2 flush between launches."""
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
@@ -345,6 +366,8 @@ def main():
                              "algorithmic_bytes": int(spmv_bytes),
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"},
                 "kernels": kernels, "clocks": cs.summary()}
+        if world == 1:
+            line["other_configs"] = small_configs(torch)
         if not args.no_cpu_baseline:
             prs, kws = workload(args.cpu_n_el)
             dt, Ns = cpu_reference_iteration(prs, kws)

@@ -179,6 +179,11 @@ class DeviceModel:
         self._pc = None
         self._sw = None
         self._sw_factored = False
+        # small systems: the factorisation costs less than the extra CG iterations a lagged
+        # preconditioner needs, so refactor whenever K has been re-assembled
+        self.eager_refactor = S.N < 100000
+        self._K_version = 0
+        self._fact_version = -1
         self.krylov_rtol = 1e-13
         self.krylov_max_it = 200000
         self.krylov_check_every = 50 if precond == "jacobi" else 5
@@ -346,6 +351,7 @@ class DeviceModel:
         if tangent:
             capi.check(lib.gf_bc_set_diag(C.byref(self.model_own_bc), 1.0, st), "gf_bc_set_diag")
             self._K_full = self.dist is None
+            self._K_version += 1
         if functionals:
             capi.check(lib.gf_reduce_wv(S.num_elements, _ptr(self.WV), _ptr(self.wv_sum), st), "gf_reduce_wv")
             self.allreduce(self.wv_sum)
@@ -503,6 +509,7 @@ class DeviceModel:
                            "gf_schwarz_factor(coarse)")
         capi.check(self.lib.gf_jacobi_setup(C.byref(cs), _ptr(self.w_dinv), st), "gf_jacobi_setup")
         self._sw_factored = True
+        self._fact_version = self._K_version
 
     def solve(self, b, x=None, rtol=None, max_it=None, refactor=None):
         """x = K^{-1} b by preconditioned CG (K symmetric => also K^{-T} b).
@@ -512,7 +519,7 @@ class DeviceModel:
             x = torch.empty_like(b)
         st = self._stream()
         cs = self.K.c_struct()
-        if refactor or not self._sw_factored:
+        if refactor or not self._sw_factored or (self.eager_refactor and self._fact_version != self._K_version):
             self.factor_preconditioner()
         pre = C.byref(self._precond_struct()) if self.precond == "schwarz" else None
         its = C.c_int(0); rel = C.c_double(0.0)
