@@ -69,7 +69,7 @@ class DeviceCsr:
 
 class DeviceModel:
     def __init__(self, problem, opt_field=(), shopt_surf_inds=(), device=None, symbolic=None,
-                 precond="schwarz", schwarz_layers=2, coarse_nc="auto", schwarz_sub=64, distributed=None):
+                 precond="schwarz", schwarz_layers=2, coarse_nc="auto", schwarz_sub=48, distributed=None):
         if not torch.cuda.is_available():
             raise capi.GoldfishError("goldfish_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = capi.load()

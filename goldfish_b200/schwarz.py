@@ -48,7 +48,7 @@ class SchwarzSetup:
             return
         self.sub = sub
         for P, (i0, i1, j0, j1) in self._subdomains(S.patches, sub):
-            # own set = a rectangle of the patch's CP grid (sub x sub nodes at most):
+            # own set = a rectangle of the patch's CP grid (sub x sub nodes at most; 48 measured best on B200 at 1 M DOF):
             # short band => short triangular-solve chains and cheap factorisation;
             # the coarse spline level carries the global coupling.
             II, JJ = np.meshgrid(np.arange(i0, i1), np.arange(j0, j1), indexing="xy")

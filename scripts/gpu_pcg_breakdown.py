@@ -8,7 +8,7 @@ from goldfish_b200.device_model import DeviceModel, _ptr
 
 n_el = int(sys.argv[1]) if len(sys.argv) > 1 else 201
 pr, kw = bench.workload(n_el)
-dm = DeviceModel(pr, coarse_nc=(int(os.environ["NC"]) if "NC" in os.environ else "auto"), **kw)
+dm = DeviceModel(pr, coarse_nc=(int(os.environ["NC"]) if "NC" in os.environ else "auto"), schwarz_sub=int(os.environ.get("SUB", "64")), schwarz_layers=int(os.environ.get("LAYERS", "2")), **kw)
 dm.u.zero_(); dm.assemble(residual=True, tangent=True)
 dm.factor_preconditioner()
 pc = dm._precond_struct(); st = dm._stream(); lib = dm.lib
