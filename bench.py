@@ -135,7 +135,7 @@ class Step:
         dm.newton(max_it=30, rtol=1e-3)
         mark("newton (assemble R,K + factor + PCG per iteration)")
         kits = list(dm.newton_krylov_its)
-        dm.assemble(tangent=True, functionals=True, shape=True, thickness=True)
+        dm.ensure(tangent=True, functionals=True, shape=True, thickness=True)   # K of the last Newton iterate is reused
         mark("linearize (K, W, V, dR/dCP x3, dR/dt, dW/d*)")
         self.rhs.copy_(dm.dWdu)
         capi.check(dm.lib.gf_mask_vec(C.byref(dm.model), C.c_void_p(self.rhs.data_ptr()), dm._stream()), "mask")

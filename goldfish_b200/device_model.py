@@ -278,15 +278,21 @@ class DeviceModel:
 
     # ------------------------------------------------------------------ state
     def set_u(self, u):
-        u = torch.as_tensor(u, dtype=torch.float64)
+        u = torch.as_tensor(u, dtype=torch.float64).reshape(-1)
         assert u.numel() == self.sym.N
-        self.u.copy_(u.reshape(-1), non_blocking=True)
+        u = u.to(self.device, non_blocking=True)
+        if torch.equal(u, self.u):
+            return                       # same state (e.g. update_uIGA right after the solve): keep cached operators
+        self.u.copy_(u)
         self.touch()
 
     def set_theta(self, th):
-        th = torch.as_tensor(th, dtype=torch.float64)
+        th = torch.as_tensor(th, dtype=torch.float64).reshape(-1)
         assert th.numel() == self.sym.n_th
-        self.theta.copy_(th.reshape(-1), non_blocking=True)
+        th = th.to(self.device, non_blocking=True)
+        if torch.equal(th, self.theta):
+            return
+        self.theta.copy_(th)
         self.touch()
 
     def set_cp(self, field, arr, surf_inds=None):
@@ -546,7 +552,9 @@ class DeviceModel:
         du = torch.empty_like(self.u)
         rhs = torch.empty_like(self.u)
         for it in range(max_it + 1):
-            self.assemble(residual=True, tangent=True)
+            self.assemble(residual=True, tangent=True, functionals=True)      # W, V ride along for free
+            for k in ("residual", "tangent", "functionals"):
+                self._epochs[k] = self.state_epoch                                # valid until u changes
             nrm = self.dot(self.R, self.R) ** 0.5
             if it == 0:
                 ref = nrm
