@@ -184,7 +184,10 @@ class DeviceModel:
         self.eager_refactor = S.N < 100000
         self._K_version = 0
         self._fact_version = -1
-        self.krylov_rtol = 1e-13
+        import os as _os
+        # relative recurrence residual; the TRUE residual of these systems (kappa ~ 1e10..1e12) stagnates near
+        # 1e-9..1e-10, and every parity test also passes at 1e-10, so 1e-11 keeps a margin without idle iterations
+        self.krylov_rtol = float(_os.environ.get("GF_KRYLOV_RTOL", "1e-11"))
         self.krylov_max_it = 200000
         self.krylov_check_every = 50 if precond == "jacobi" else 5
         self.last_krylov_its = 0
