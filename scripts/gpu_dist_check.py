@@ -25,5 +25,9 @@ if rank == 0:
     print("u", rel(dm.u, ref.u), "lam", rel(step.lam, rstep.lam), "gT", rel(step.gT, rstep.gT),
           "gP", [rel(a, b) for a, b in zip(step.gP, rstep.gP)], "W,V", dm.wv_sum.tolist(), ref.wv_sum.tolist())
     print("step time sharded %.3f s, single %.3f s" % (t1 - t0, t3 - t2))
+    import json
+    print("RESULT " + json.dumps({"u": rel(dm.u, ref.u), "lam": rel(step.lam, rstep.lam), "gT": rel(step.gT, rstep.gT),
+                                  "gP": max(rel(a, b) for a, b in zip(step.gP, rstep.gP)),
+                                  "its_sharded": step.info["krylov_its"], "its_single": rstep.info["krylov_its"]}))
 dist.barrier()
 dist.destroy_process_group()
