@@ -201,4 +201,5 @@ def test_patch_sharded_two_gpus_match_single_gpu():
     import json
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT ")][0][7:])
     assert max(res["u"], res["lam"], res["gT"], res["gP"]) < 1e-7
-    assert res["its_sharded"] == res["its_single"]
+    # same preconditioner, all-reduce changes the summation order: counts agree up to the check interval
+    assert all(abs(a - b) <= 10 for a, b in zip(res["its_sharded"], res["its_single"]))
