@@ -628,13 +628,32 @@ k_shell_k2(GfModel M, GfShellOut O, int what, int color_begin, int color_count) 
     for (int h = 0; h < 2; ++h) {
       if (q0 + h >= nq) break;
       const double wq = M.qw[q0 + h] * area;
-      for (int o = lane; o < 720; o += 32) {
-        const int m = o / 48, cb = o - m * 48;
-        const int b = cb / 3, j = cb - 3 * b;
-        double s = 0.0;
+      {
+        // G[m][3b+j] = w sum_l H[m][(l,j)] Phi[1+l][b]: lane = b + 16 s owns column b;
+        // s = 0: j = 0 (all m) and j = 2 (m < 8); s = 1: j = 1 (all m) and j = 2 (m >= 8).
+        // Fully unrolled: no index arithmetic, the five Phi values stay in registers and the
+        // H loads are warp-wide broadcasts.
+        double pl[5];
 #pragma unroll
-        for (int l = 0; l < 5; ++l) s = fma(S.Hc[h][m][l * 3 + j], S.Phi[h][1 + l][b], s);
-        S.G[m][cb] = wq * s;
+        for (int l = 0; l < 5; ++l) pl[l] = wq * S.Phi[h][1 + l][an];
+        const int j0 = half;                       // 0 or 1
+#pragma unroll
+        for (int m = 0; m < 15; ++m) {
+          double s0 = 0.0;
+#pragma unroll
+          for (int l = 0; l < 5; ++l) s0 = fma(S.Hc[h][m][l * 3 + j0], pl[l], s0);
+          S.G[m][3 * an + j0] = s0;
+        }
+#pragma unroll
+        for (int mm = 0; mm < 8; ++mm) {
+          const int m = mm + 8 * half;
+          if (m < 15) {
+            double s2 = 0.0;
+#pragma unroll
+            for (int l = 0; l < 5; ++l) s2 = fma(S.Hc[h][m][l * 3 + 2], pl[l], s2);
+            S.G[m][3 * an + 2] = s2;
+          }
+        }
       }
       __syncwarp();
 #pragma unroll
@@ -887,13 +906,29 @@ k_shell_p2(GfModel M, GfShellOut O, int color_begin, int color_count) {
       const double wq = M.qw[q0 + h] * area;
       const double tq = S.g[h][15];
       if (PT == 1) {
-        for (int o = lane; o < 720; o += 32) {
-          const int m = o / 48, fb = o - m * 48;
-          const int f = fb >> 4, b = fb & 15;
-          double s = 0.0;
+        {
+          // G_f[m][16 f + b]: lane = b + 16 s; s = 0: f = 0 (all m), f = 2 (m < 8); s = 1: f = 1, f = 2 (m >= 8)
+          double pl[5];
 #pragma unroll
-          for (int l = 0; l < 5; ++l) s = fma(S.Hc[h][m][l * 3 + f], S.Phi[h][1 + l][b], s);
-          S.G[m][fb] = wq * s;
+          for (int l = 0; l < 5; ++l) pl[l] = wq * S.Phi[h][1 + l][an];
+          const int f0 = half;
+#pragma unroll
+          for (int m = 0; m < 15; ++m) {
+            double s0 = 0.0;
+#pragma unroll
+            for (int l = 0; l < 5; ++l) s0 = fma(S.Hc[h][m][l * 3 + f0], pl[l], s0);
+            S.G[m][16 * f0 + an] = s0;
+          }
+#pragma unroll
+          for (int mm = 0; mm < 8; ++mm) {
+            const int m = mm + 8 * half;
+            if (m < 15) {
+              double s2 = 0.0;
+#pragma unroll
+              for (int l = 0; l < 5; ++l) s2 = fma(S.Hc[h][m][l * 3 + 2], pl[l], s2);
+              S.G[m][32 + an] = s2;
+            }
+          }
         }
         __syncwarp();
 #pragma unroll

@@ -191,7 +191,9 @@ class NonMatchingOpt:
         """The device model is built on first use, after all set_* calls."""
         if self._dm is None:
             self.problem = self._problem()
-            self._dm = DeviceModel(self.problem, self.opt_field, self.shopt_surf_inds, device=self.device)
+            # a caller that already ran the symbolic phase for this topology may hand it over (`_symbolic`)
+            self._dm = DeviceModel(self.problem, self.opt_field, self.shopt_surf_inds, device=self.device,
+                                   symbolic=getattr(self, "_symbolic", None))
             S = self._dm.sym
             dv = self._dm.device
             self.vec_iga_nest = DeviceVec.zeros(self.vec_iga_dof_list, dv, self._dm)
