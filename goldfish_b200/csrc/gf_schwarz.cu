@@ -319,14 +319,8 @@ __device__ __forceinline__ void sw_prefetch(const GfSchwarz& S, int i, int j, in
 // bound by FP32->FP64 conversions (16/clk/SM) and FP64 shuffle reductions, not by HBM.  The
 // block GEMVs therefore run in FP32 (FFMA, x converted once per step, 4 threads per row /
 // column, 2-step reductions); results are accumulated into the FP64 vectors.
-__global__ void __launch_bounds__(256)
-k_sw_solve(GfSchwarz Sf, int G_f, int first_block, int nf, GfSchwarz Sc, int G_c) {
-  const bool is_c = (int)blockIdx.x >= nf * G_f;
-  const GfSchwarz& S = is_c ? Sc : Sf;
-  const int G = is_c ? G_c : G_f;
-  const int bx = is_c ? (int)blockIdx.x - nf * G_f : (int)blockIdx.x;
-  const int i = is_c ? 0 : first_block + bx / G, cta = bx % G;
-  extern __shared__ __align__(16) float pre[];     // [PF][64][LDS] floats
+__device__ __forceinline__ void sw_group_solve(const GfSchwarz& S, const int i, const int cta, const int G, float* pre) {
+  // pre: [PF][64][LDS] floats of dynamic shared memory
   __shared__ double xs[NB];
   __shared__ __align__(16) float xf[NB];
   __shared__ float red[4][NB];
@@ -450,6 +444,145 @@ k_sw_solve(GfSchwarz Sf, int G_f, int first_block, int nf, GfSchwarz Sc, int G_c
 }
 
 __global__ void __launch_bounds__(256)
+k_sw_solve(GfSchwarz Sf, int G_f, int first_block, int nf, GfSchwarz Sc, int G_c) {
+  extern __shared__ __align__(16) unsigned char sw_smem[];
+  float* pre = reinterpret_cast<float*>(sw_smem);
+  if ((int)blockIdx.x >= nf * G_f) sw_group_solve(Sc, 0, (int)blockIdx.x - nf * G_f, G_c, pre);
+  else sw_group_solve(Sf, first_block + (int)blockIdx.x / G_f, (int)blockIdx.x % G_f, G_f, pre);
+}
+
+// ---- one CTA per block: the whole block-local vector lives in shared memory -------------
+// With >= ~1 block per SM there is nothing to gain from splitting a block over CTAs: a single
+// CTA needs no inter-CTA barrier (two bar.sync per step instead of an L2 round trip), no atomics
+// and no s-vector; the factor is streamed exactly once per sweep, the next panels are pulled
+// into L2 while the current step computes.  Backward runs in GATHER form over the same column
+// panels the forward sweep uses:  x_j = w_j - sum_k M(j+k, j)^T x_{j+k}.
+constexpr int XW = 32;        // ring of FP32 copies of the last XW solution blocks (needs max_mb < XW)
+constexpr int SW1_PD = 2;     // panels prefetched ahead into L2
+
+__device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void sw1_prefetch(const float* panel, int mb, const double* D) {
+  const char* p = reinterpret_cast<const char*>(panel + NB2);          // tile k = 0 is not used by the sweeps
+  const int lines = mb * (NB2 * 4 / 128);
+  for (int l = threadIdx.x; l < lines; l += 256) l2_prefetch(p + (size_t)l * 128);
+  if (D) l2_prefetch(reinterpret_cast<const char*>(D) + (size_t)threadIdx.x * 128);   // 32 KB = 256 lines
+}
+
+__device__ __forceinline__ void sw_single_solve(const GfSchwarz& S, const int i, const double* __restrict__ r, double* ys) {
+  __shared__ __align__(16) float xf1[NB];
+  __shared__ __align__(16) float xw[XW * NB];
+  __shared__ double red1[4][NB];
+  const int tid = threadIdx.x;
+  const int nbr = S.nbr[i], n_pad = S.n_pad[i];
+  const int32_t* mbj = S.mbj + S.off_j[i];
+  const int64_t* offc = S.off_col + S.off_j[i];
+  const double* invd = S.invd + S.off_inv[i];
+  const int32_t* glob = S.glob + S.off_y[i];
+  const int fr = tid >> 2, fq = tid & 3;           // forward: row fr, quarter fq (16 columns)
+  const int bc = tid & 63, bq = tid >> 6;          // transposed products: column bc, quarter bq (16 rows)
+  for (int p = 0; p < SW1_PD && p < nbr; ++p) sw1_prefetch(S.band32 + offc[p], mbj[p], invd + (size_t)p * NB2);
+  for (int l = tid; l < n_pad; l += 256) { const int g = glob[l]; ys[l] = (g >= 0) ? r[g] : 0.0; }
+  __syncthreads();
+  // ---------------- forward: y_{j+k} -= M(j+k, j) y_j ; then w_j = D_j y_j replaces y_j ----------------
+  for (int j = 0; j < nbr; ++j) {
+    const int mb = mbj[j];
+    if (tid < NB) xf1[tid] = (float)ys[j * NB + tid];
+    if (j + SW1_PD < nbr) sw1_prefetch(S.band32 + offc[j + SW1_PD], mbj[j + SW1_PD], invd + (size_t)(j + SW1_PD) * NB2);
+    __syncthreads();
+    float xr[16];
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(xf1 + fq * 16 + c);
+      xr[c] = v.x; xr[c + 1] = v.y; xr[c + 2] = v.z; xr[c + 3] = v.w;
+    }
+    const float* panel = S.band32 + offc[j];
+    for (int k = 1; k <= mb; k += 4) {
+      float4 m[4][4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (k + t <= mb) {
+          const float4* p = reinterpret_cast<const float4*>(panel + (size_t)(k + t) * NB2 + fr * NB + fq * 16);
+          m[t][0] = __ldcs(p); m[t][1] = __ldcs(p + 1); m[t][2] = __ldcs(p + 2); m[t][3] = __ldcs(p + 3);
+        }
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (k + t <= mb) {
+          float a = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            a = fmaf(m[t][c].x, xr[4 * c], a); a = fmaf(m[t][c].y, xr[4 * c + 1], a);
+            a = fmaf(m[t][c].z, xr[4 * c + 2], a); a = fmaf(m[t][c].w, xr[4 * c + 3], a);
+          }
+          a += __shfl_xor_sync(0xffffffffu, a, 1);
+          a += __shfl_xor_sync(0xffffffffu, a, 2);
+          if (fq == 0) ys[(j + k + t) * NB + fr] -= (double)a;      // one owner per entry and step
+        }
+    }
+    {   // D_j is symmetric: read it row-wise as its own transpose (coalesced over the column index)
+      const double* D = invd + (size_t)j * NB2 + (size_t)(bq * 16) * NB + bc;
+      const double* yj = ys + j * NB + bq * 16;
+      double d[16];
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) d[rr] = __ldcs(D + rr * NB);
+      double acc = 0.0;
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) acc = fma(d[rr], yj[rr], acc);
+      red1[bq][bc] = acc;
+    }
+    __syncthreads();
+    if (tid < NB) ys[j * NB + tid] = (red1[0][tid] + red1[1][tid]) + (red1[2][tid] + red1[3][tid]);
+  }
+  // ---------------- backward: x_j = w_j - sum_k M(j+k, j)^T x_{j+k} ----------------
+  for (int j = nbr - 1; j >= 0; --j) {
+    const int mb = mbj[j];
+    if (j - SW1_PD >= 0) sw1_prefetch(S.band32 + offc[j - SW1_PD], mbj[j - SW1_PD], nullptr);
+    const float* panel = S.band32 + offc[j];
+    double acc = 0.0;
+    for (int k = 1; k <= mb; k += 4) {
+      float m[4][16];
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (k + t <= mb) {
+          const float* p = panel + (size_t)(k + t) * NB2 + (bq * 16) * NB + bc;
+#pragma unroll
+          for (int rr = 0; rr < 16; ++rr) m[t][rr] = __ldcs(p + rr * NB);
+        }
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (k + t <= mb) {
+          const float4* xv = reinterpret_cast<const float4*>(xw + ((j + k + t) & (XW - 1)) * NB + bq * 16);
+          float a = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 v = xv[c];
+            a = fmaf(m[t][4 * c], v.x, a); a = fmaf(m[t][4 * c + 1], v.y, a);
+            a = fmaf(m[t][4 * c + 2], v.z, a); a = fmaf(m[t][4 * c + 3], v.w, a);
+          }
+          acc += (double)a;
+        }
+    }
+    red1[bq][bc] = acc;
+    __syncthreads();
+    if (tid < NB) {
+      const double xv = ys[j * NB + tid] - ((red1[0][tid] + red1[1][tid]) + (red1[2][tid] + red1[3][tid]));
+      ys[j * NB + tid] = xv;
+      xw[(j & (XW - 1)) * NB + tid] = (float)xv;
+    }
+    __syncthreads();
+  }
+  double* y = S.y + S.off_y[i];
+  for (int l = tid; l < n_pad; l += 256) y[l] = ys[l];
+}
+
+// CTAs [0, G_c) sweep the coarse block as one barrier group; every other CTA owns one fine block.
+__global__ void __launch_bounds__(256, 2)
+k_sw_solve1(GfSchwarz Sf, const double* __restrict__ r_f, int first_block, GfSchwarz Sc, int G_c) {
+  extern __shared__ __align__(16) unsigned char sw_smem[];
+  if ((int)blockIdx.x < G_c) sw_group_solve(Sc, 0, (int)blockIdx.x, G_c, reinterpret_cast<float*>(sw_smem));
+  else sw_single_solve(Sf, first_block + (int)blockIdx.x - G_c, r_f, reinterpret_cast<double*>(sw_smem));
+}
+
+__global__ void __launch_bounds__(256)
 k_dot_slot0(int64_t n, const double* x, const double* y, double* partial2) {
   __shared__ double sh[32];
   double s = 0.0;
@@ -523,41 +656,95 @@ static int sw_caps(int* sms_out, int* occ_out) {
   return sms * occ;
 }
 
+// Single-CTA-per-block path: capacity and dynamic shared memory of k_sw_solve1 for blocks of
+// at most max_n_pad dofs riding with (or without) a coarse group.  Returns 0 if it does not fit.
+static int sw1_caps(int max_n_pad, bool with_coarse, size_t* smem_out) {
+  size_t smem = (size_t)max_n_pad * sizeof(double);
+  if (with_coarse && smem < PF * PBLK * sizeof(float)) smem = PF * PBLK * sizeof(float);
+  static size_t smem_set = 0, smem_cached = 0;
+  static int cap_cached = 0;
+  *smem_out = smem;
+  if (smem == smem_cached) return cap_cached;
+  int dev = 0, sms = 0, lim = 0, occ = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaFuncAttributes fa;
+  int cap = 0;
+  if (cudaFuncGetAttributes(&fa, k_sw_solve1) == cudaSuccess && smem + fa.sharedSizeBytes <= (size_t)lim) {
+    bool ok = true;
+    if (smem > smem_set) {
+      ok = cudaFuncSetAttribute(k_sw_solve1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+      if (ok) smem_set = smem;
+    }
+    if (ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sw_solve1, 256, smem) == cudaSuccess && occ >= 1) cap = sms * occ;
+  }
+  cudaGetLastError();                              // a failed probe must not poison the next launch check
+  smem_cached = smem; cap_cached = cap;
+  return cap;
+}
+
 // z_f = sum_i R_i^T A_i^-1 R_i r_f  (fine blocks of Sf)  and, if Sc != NULL, z_c = Kc^-1 r_c
 // (single block of Sc) with both sets of triangular sweeps running concurrently.
 extern "C" int gf_schwarz_apply2(const GfSchwarz* Sf, const double* r_f, double* z_f, int64_t n_f,
                                  const GfSchwarz* Sc, const double* r_c, double* z_c, int64_t n_c, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  int g = (int)((Sf->n_y + 255) / 256); if (g > 2048) g = 2048;
-  k_sw_gather_in<<<g, 256, 0, st>>>(*Sf, r_f);
-  cudaError_t e = cudaMemsetAsync(Sf->barrier, 0, sizeof(unsigned) * Sf->nblocks, st);
+  cudaError_t e = cudaSuccess;
+  int sms, occ;
+  const int cap = sw_caps(&sms, &occ);           // all CTAs of one cooperative launch must be co-resident
+  GfSchwarz Sfv = *Sf, Scv = Sc ? *Sc : *Sf;
+  static int dbg = -1, single = -1;
+  if (dbg < 0) { dbg = 0; if (const char* ev = getenv("GF_SW_DEBUG")) dbg = atoi(ev); }
+  if (single < 0) { single = 2; if (const char* ev = getenv("GF_SW_SINGLE")) single = atoi(ev); }   // 0 off, 1 on, 2 auto
+  Sfv.debug_flags = Sf->debug_flags | dbg; Scv.debug_flags = dbg;
+  int mode = single;                              // GfSchwarz.debug_flags: 4 forces one CTA per block, 8 forces CTA groups
+  if (Sfv.debug_flags & 4) mode = 1;
+  if (Sfv.debug_flags & 8) mode = 0;
+  int G_c = 0;
   if (Sc) {
     int gc = (int)((Sc->n_y + 255) / 256); if (gc > 2048) gc = 2048;
     k_sw_gather_in<<<gc, 256, 0, st>>>(*Sc, r_c);
-    if (e == cudaSuccess) e = cudaMemsetAsync(Sc->barrier, 0, sizeof(unsigned) * Sc->nblocks, st);
+    e = cudaMemsetAsync(Sc->barrier, 0, sizeof(unsigned) * Sc->nblocks, st);
+    if (e != cudaSuccess) return set_cuda_error(e, "gf_schwarz_apply memset");
     count_launch(1);
+    G_c = cap / 6; if (G_c > Sc->max_mb) G_c = Sc->max_mb; if (G_c < 1) G_c = 1;
   }
-  if (e != cudaSuccess) return set_cuda_error(e, "gf_schwarz_apply memset");
-  int sms, occ;
-  const int cap = sw_caps(&sms, &occ);           // all CTAs of one launch must be co-resident
-  GfSchwarz Sfv = *Sf, Scv = Sc ? *Sc : *Sf;
-  static int dbg = -1;
-  if (dbg < 0) { dbg = 0; if (const char* ev = getenv("GF_SW_DEBUG")) dbg = atoi(ev); }
-  Sfv.debug_flags = dbg; Scv.debug_flags = dbg;
-  int G_c = 0;
-  if (Sc) { G_c = cap / 6; if (G_c > Sc->max_mb) G_c = Sc->max_mb; if (G_c < 1) G_c = 1; }
-  int G = (cap - G_c) / Sf->nblocks;
-  if (G > Sf->max_mb) G = Sf->max_mb;            // one panel block per CTA and step is enough
-  if (G < 1) G = 1;
-  const int per_launch = (cap - G_c) / G;        // fine blocks per cooperative launch
-  for (int b0 = 0; b0 < Sf->nblocks; b0 += per_launch) {
-    int nb_l = Sf->nblocks - b0; if (nb_l > per_launch) nb_l = per_launch;
-    int first = b0;
-    int gcl = (b0 == 0) ? G_c : 0;               // the coarse block rides along with the first batch
-    void* args[] = {&Sfv, &G, &first, &nb_l, &Scv, &gcl};
-    e = cudaLaunchCooperativeKernel((void*)k_sw_solve, dim3(nb_l * G + gcl), dim3(256), args, PF * PBLK * sizeof(float), st);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchCooperativeKernel(k_sw_solve)");
+  // one CTA per block whenever a block's vector fits in shared memory (otherwise: G CTAs per block)
+  size_t smem1 = 0;
+  int cap1 = 0;
+  if (mode && Sf->max_mb < XW) cap1 = sw1_caps(Sf->max_n_pad, Sc != nullptr, &smem1);
+  if (cap1 > G_c) {
+    for (int b0 = 0; b0 < Sf->nblocks;) {
+      const int gcl = (b0 == 0) ? G_c : 0;       // the coarse group rides along with the first batch
+      int nb_l = Sf->nblocks - b0;
+      if (nb_l > cap1 - gcl) nb_l = cap1 - gcl;
+      int first = b0;
+      void* args[] = {&Sfv, &r_f, &first, &Scv, (void*)&gcl};
+      if (gcl) e = cudaLaunchCooperativeKernel((void*)k_sw_solve1, dim3(nb_l + gcl), dim3(256), args, smem1, st);
+      else { k_sw_solve1<<<nb_l, 256, smem1, st>>>(Sfv, r_f, first, Scv, 0); e = cudaGetLastError(); }
+      if (e != cudaSuccess) return set_cuda_error(e, "launch k_sw_solve1");
+      count_launch(1);
+      b0 += nb_l;
+    }
+  } else {
+    int g = (int)((Sf->n_y + 255) / 256); if (g > 2048) g = 2048;
+    k_sw_gather_in<<<g, 256, 0, st>>>(*Sf, r_f);
+    e = cudaMemsetAsync(Sf->barrier, 0, sizeof(unsigned) * Sf->nblocks, st);
+    if (e != cudaSuccess) return set_cuda_error(e, "gf_schwarz_apply memset");
     count_launch(1);
+    int G = (cap - G_c) / Sf->nblocks;
+    if (G > Sf->max_mb) G = Sf->max_mb;            // one panel block per CTA and step is enough
+    if (G < 1) G = 1;
+    const int per_launch = (cap - G_c) / G;        // fine blocks per cooperative launch
+    for (int b0 = 0; b0 < Sf->nblocks; b0 += per_launch) {
+      int nb_l = Sf->nblocks - b0; if (nb_l > per_launch) nb_l = per_launch;
+      int first = b0;
+      int gcl = (b0 == 0) ? G_c : 0;               // the coarse block rides along with the first batch
+      void* args[] = {&Sfv, &G, &first, &nb_l, &Scv, &gcl};
+      e = cudaLaunchCooperativeKernel((void*)k_sw_solve, dim3(nb_l * G + gcl), dim3(256), args, PF * PBLK * sizeof(float), st);
+      if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchCooperativeKernel(k_sw_solve)");
+      count_launch(1);
+    }
   }
   int g2 = (int)((n_f + 255) / 256); if (g2 > 2048) g2 = 2048;
   k_sw_gather_out<<<g2, 256, 0, st>>>(*Sf, z_f, n_f);

@@ -69,7 +69,7 @@ class DeviceCsr:
 
 class DeviceModel:
     def __init__(self, problem, opt_field=(), shopt_surf_inds=(), device=None, symbolic=None,
-                 precond="schwarz", schwarz_layers=2, coarse_nc="auto", schwarz_sub=48, distributed=None):
+                 precond="schwarz", schwarz_layers=2, coarse_nc="auto", schwarz_sub=(24, 96), distributed=None):
         if not torch.cuda.is_available():
             raise capi.GoldfishError("goldfish_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = capi.load()
@@ -168,11 +168,17 @@ class DeviceModel:
         self.precond = precond
         self.schwarz_layers = schwarz_layers
         self.schwarz_sub = schwarz_sub
+        import os as _os0
+        if _os0.environ.get("GF_SW_SUB"):                  # tuning experiments: "48" or "24,96"
+            v = [int(x) for x in _os0.environ["GF_SW_SUB"].split(",")]
+            self.schwarz_sub = v[0] if len(v) == 1 else (v[0], v[1])
+        if _os0.environ.get("GF_SW_LAYERS"):
+            self.schwarz_layers = int(_os0.environ["GF_SW_LAYERS"])
         max_ne = max(max(P.neu, P.nev) for P in S.patches)
         if coarse_nc == "auto":
             # the coarse sweeps run beside the fine ones: keep their chain shorter than the fine chains
             # (which shrink per GPU when the blocks are spread over several ranks)
-            cap_nc = 24 if self.world < 4 else 16
+            cap_nc = 20 if self.world < 4 else 16
             coarse_nc = 0 if max_ne < 16 else int(min(cap_nc, max(8, max_ne // 8)))
         self.coarse_nc = int(coarse_nc) if precond == "schwarz" else 0
         self.problem = problem
@@ -483,6 +489,11 @@ class DeviceModel:
             self._sw = (s, t, step_mb, A)
         return self._sw[0]
 
+    def set_sweep_mode(self, mode):
+        """Triangular-sweep kernel of the fine Schwarz blocks: "auto" (by block count), "single" (one CTA
+        per block, vector in shared memory) or "group" (CTA group per block, global-memory barrier)."""
+        self._schwarz().debug_flags = {"auto": 0, "single": 4, "group": 8}[mode]
+
     def _dist_struct(self):
         if getattr(self, "_dist_c", None) is None:
             d = capi.GfDist()
@@ -519,6 +530,16 @@ class DeviceModel:
         capi.check(self.lib.gf_jacobi_setup(C.byref(cs), _ptr(self.w_dinv), st), "gf_jacobi_setup")
         self._sw_factored = True
         self._fact_version = self._K_version
+
+    def precond_apply(self, r, z=None):
+        """z = M^-1 r with the factored preconditioner (what every CG iteration calls)."""
+        if z is None:
+            z = torch.empty_like(r)
+        if not self._sw_factored:
+            self.factor_preconditioner()
+        capi.check(self.lib.gf_precond_apply(C.byref(self._precond_struct()), _ptr(r), _ptr(z), self.sym.N, self._stream()),
+                   "gf_precond_apply")
+        return z
 
     def solve(self, b, x=None, rtol=None, max_it=None, refactor=None):
         """x = K^{-1} b by preconditioned CG (K symmetric => also K^{-T} b).

@@ -20,7 +20,7 @@ NB = 64
 
 
 class SchwarzSetup:
-    def __init__(self, sym, layers=2, single_block=False, sub=48):
+    def __init__(self, sym, layers=2, single_block=False, sub=(24, 96)):
         S = sym
         self.sym, self.layers = sym, layers
         n_s = S.n_scalar
@@ -48,7 +48,8 @@ class SchwarzSetup:
             return
         self.sub = sub
         for P, (i0, i1, j0, j1) in self._subdomains(S.patches, sub):
-            # own set = a rectangle of the patch's CP grid (sub x sub nodes at most; 48 measured best on B200 at 1 M DOF):
+            # own set = a rectangle of the patch's CP grid (at most sub[0] x sub[1] nodes; 24 x 96 measured best on B200 at
+            # 1 M DOF: the narrow side sets the band width, the long side keeps the overlap volume down):
             # short band => short triangular-solve chains and cheap factorisation;
             # the coarse spline level carries the global coupling.
             II, JJ = np.meshgrid(np.arange(i0, i1), np.arange(j0, j1), indexing="xy")
@@ -94,9 +95,10 @@ class SchwarzSetup:
 
     @staticmethod
     def _subdomains(patches, sub):
-        """Rectangles (i0, i1, j0, j1) of at most sub x sub control points tiling each patch."""
+        """Rectangles (i0, i1, j0, j1) of at most sub x sub (or sub[0] x sub[1]) control points tiling each patch."""
+        sub_u, sub_v = (sub, sub) if np.isscalar(sub) else sub
         for P in patches:
-            su = max(1, int(np.ceil(P.n_u / sub))); sv = max(1, int(np.ceil(P.n_v / sub)))
+            su = max(1, int(np.ceil(P.n_u / sub_u))); sv = max(1, int(np.ceil(P.n_v / sub_v)))
             eu = np.round(np.linspace(0, P.n_u, su + 1)).astype(int); ev = np.round(np.linspace(0, P.n_v, sv + 1)).astype(int)
             for b in range(sv):
                 for a in range(su):

@@ -182,7 +182,8 @@ int gf_spmv_t(const GfCsr* A, const GfCsrT* At, const double* x, double* y, doub
 typedef struct GfSchwarz {
   int32_t nblocks, nb;            /* nb = 64                                          */
   int32_t max_nbr, max_mb, max_n_pad;
-  int32_t debug_flags;            /* 0 in production; timing experiments: 1 skip block GEMVs, 2 skip barriers */
+  int32_t debug_flags;            /* 0 in production; timing experiments: 1 skip block GEMVs, 2 skip barriers;
+                                     sweep kernel choice: 4 = one CTA per block, 8 = CTA group per block (default: by block count) */
   int64_t n_y, band_len;          /* total padded local dofs; band storage length     */
   const int32_t* n_pad;           /* [nblocks] padded local size (multiple of nb)     */
   const int32_t* nbr;             /* [nblocks] block rows                             */
@@ -209,7 +210,9 @@ typedef struct GfSchwarz {
 } GfSchwarz;
 int gf_schwarz_factor(const GfSchwarz* s, const GfCsr* K, void* stream);
 int gf_schwarz_apply(const GfSchwarz* s, const double* r, double* z, int64_t n, void* stream);
-/* fine blocks + one coarse block, triangular sweeps of both in one cooperative launch */
+/* fine blocks + one coarse block, triangular sweeps of both in one cooperative launch.  With at least
+ * half as many fine blocks as SMs every fine block is swept by ONE CTA out of shared memory (r_f is
+ * gathered by the kernel); otherwise a group of CTAs shares each block through a global-memory barrier. */
 int gf_schwarz_apply2(const GfSchwarz* fine, const double* r_f, double* z_f, int64_t n_f,
                       const GfSchwarz* coarse, const double* r_c, double* z_c, int64_t n_c, void* stream);
 int gf_dot_slot0(int64_t n, const double* x, const double* y, double* partial2, int grid, void* stream);
