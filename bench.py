@@ -296,9 +296,10 @@ def main():
     l0 = lib.gf_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as cs:
+        step_timers = [[] for _ in range(args.steps)]     # four event records per step: phase split of the timed steps
         e0.record()
-        for _ in range(args.steps):
-            step()
+        for k in range(args.steps):
+            step(step_timers[k])
         e1.record()
         barrier()
     launches = lib.gf_launch_count() - l0
@@ -339,9 +340,12 @@ def main():
     asm_ms = time_kernel(torch, lambda: dm.assemble(tangent=True, residual=True), 5, flush)
     nq = S.nq
     asm_flops = S.num_elements * nq * 29376.0
-    timers = []
-    step(timers); torch.cuda.synchronize()
-    phases = {timers[i][0]: round(timers[i - 1][1].elapsed_time(timers[i][1]), 2) for i in range(1, len(timers))}
+    torch.cuda.synchronize()
+    phases = {}
+    for timers in step_timers:
+        for i in range(1, len(timers)):
+            phases[timers[i][0]] = phases.get(timers[i][0], 0.0) + timers[i - 1][1].elapsed_time(timers[i][1]) / len(step_timers)
+    phases = {k: round(v, 2) for k, v in phases.items()}
     fac_ms = time_kernel(torch, lambda: dm.factor_preconditioner(), 2, flush)
     kernels = {"phase_ms": phases, "precond_factor_ms": fac_ms, "spmv_ms": spmv_ms, "spmv_gbs": achieved,
                "assemble_RK_ms": asm_ms, "assemble_RK_material_tflops": asm_flops / (asm_ms * 1e-3) / 1e12,

@@ -19,6 +19,7 @@
 #include "gf_common.cuh"
 #include <stdlib.h>
 #include <cuda_pipeline.h>
+#include <cooperative_groups.h>
 
 namespace gf {
 
@@ -582,6 +583,173 @@ k_sw_solve1(GfSchwarz Sf, const double* __restrict__ r_f, int first_block, GfSch
   else sw_single_solve(Sf, first_block + (int)blockIdx.x - G_c, r_f, reinterpret_cast<double*>(sw_smem));
 }
 
+// ---- the coarse block on ONE thread-block cluster ----------------------------------------
+// The coarse block is a single long dependency chain (2 x nbr steps); with CTAs that only share
+// global memory every step costs two L2 round trips plus a polled barrier (~3 us measured).  On a
+// cluster the step is: the owner of block row j broadcasts its 64 FP32 values into every CTA's
+// shared memory (DSMEM), barrier.cluster, every CTA updates the rows IT owns out of its own
+// shared memory.  Block row R lives in CTA R % CL ("owner computes"): no atomics, no global
+// traffic on the chain, tiles arrive through a 3-step cp.async ring.
+//   forward : y_R -= M(R, j) y_j          for the tiles (R, j) with R % CL == rank
+//   backward: x_C -= M(j, C)^T x_j        for the tiles (j, C) with C % CL == rank
+namespace cg = cooperative_groups;
+
+__device__ __forceinline__ int cc_k0(int c, int j, int CL, bool backward) {
+  int d = (backward ? (j - c) : (c - j)) % CL;
+  if (d < 0) d += CL;
+  return d == 0 ? CL : d;
+}
+__device__ __forceinline__ void cc_prefetch(const float* __restrict__ band32, const int64_t* __restrict__ offc,
+                                            const int32_t* __restrict__ lim, int nbr, int j, int c, int CL,
+                                            bool backward, float* stage) {
+  if (j >= 0 && j < nbr) {
+    const int kmax = lim[j];
+    int t = 0;
+    for (int k = cc_k0(c, j, CL, backward); k <= kmax; k += CL, ++t) {
+      const float* src = band32 + (backward ? offc[j - k] : offc[j]) + (size_t)k * NB2;
+      float* dst = stage + t * PBLK;
+      for (int e = threadIdx.x; e < NB2 / 4; e += 256)
+        __pipeline_memcpy_async(dst + (e >> 4) * LDS + (e & 15) * 4, src + e * 4, 16);
+    }
+  }
+  __pipeline_commit();                       // one group per step, empty or not
+}
+
+__global__ void __launch_bounds__(256, 1)
+k_sw_coarse_cluster(GfSchwarz S, int TPS) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), c = (int)cluster.block_rank();
+  extern __shared__ __align__(16) unsigned char sw_smem[];
+  float* ring = reinterpret_cast<float*>(sw_smem);                                       // [3][TPS][PBLK]
+  double* yl = reinterpret_cast<double*>(sw_smem + (size_t)3 * TPS * PBLK * sizeof(float));  // [rows_loc][NB]
+  __shared__ __align__(16) float xb[2][NB];
+  __shared__ float redc[4][NB];
+  __shared__ double redd[4][NB];
+  const int nbr = S.nbr[0];
+  const double* invd = S.invd + S.off_inv[0];
+  double* y = S.y + S.off_y[0];
+  const int tid = threadIdx.x;
+  const int fr = tid >> 2, fq = tid & 3;
+  const int bc = tid & 63, bq = tid >> 6;
+  const int rows_loc = (nbr + CL - 1) / CL;
+  const size_t stage_sz = (size_t)TPS * PBLK;
+  // the envelope tables are read on the dependency chain: keep them in shared memory
+  // (cluster.sync invalidates L1, every global read after it would be an L2 round trip)
+  int64_t* offc = reinterpret_cast<int64_t*>(yl + (size_t)rows_loc * NB);                 // [nbr]
+  int32_t* mbj = reinterpret_cast<int32_t*>(offc + nbr);                                  // [nbr]
+  int32_t* rlen = mbj + nbr;                                                              // [nbr]
+  for (int t = tid; t < nbr; t += 256) {
+    offc[t] = S.off_col[S.off_j[0] + t]; mbj[t] = S.mbj[S.off_j[0] + t]; rlen[t] = S.rlen[S.off_j[0] + t];
+  }
+  __syncthreads();
+
+  cc_prefetch(S.band32, offc, mbj, nbr, 0, c, CL, false, ring);
+  cc_prefetch(S.band32, offc, mbj, nbr, 1, c, CL, false, ring + stage_sz);
+  for (int idx = tid; idx < rows_loc * NB; idx += 256) {
+    const int R = (idx / NB) * CL + c;
+    yl[idx] = (R < nbr) ? y[(size_t)R * NB + (idx % NB)] : 0.0;
+  }
+  __syncthreads();
+  if (c == 0 && tid < NB) {
+    const float v = (float)yl[tid];
+    for (int q = 0; q < CL; ++q) cluster.map_shared_rank(&xb[0][0], q)[tid] = v;
+  }
+  cluster.sync();
+  // ---------------- forward ----------------
+  for (int j = 0; j < nbr; ++j) {
+    cc_prefetch(S.band32, offc, mbj, nbr, j + 2, c, CL, false, ring + ((j + 2) % 3) * stage_sz);
+    __pipeline_wait_prior(2);
+    __syncthreads();
+    float xr[16];
+#pragma unroll
+    for (int cc = 0; cc < 16; cc += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(&xb[j & 1][fq * 16 + cc]);
+      xr[cc] = v.x; xr[cc + 1] = v.y; xr[cc + 2] = v.z; xr[cc + 3] = v.w;
+    }
+    const float* stage = ring + (j % 3) * stage_sz;
+    const int kmax = mbj[j];
+    int t = 0;
+    for (int k = cc_k0(c, j, CL, false); k <= kmax; k += CL, ++t) {
+      const float* p = stage + t * PBLK + fr * LDS + fq * 16;
+      float a = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 16; cc += 4) {
+        const float4 m = *reinterpret_cast<const float4*>(p + cc);
+        a = fmaf(m.x, xr[cc], a); a = fmaf(m.y, xr[cc + 1], a); a = fmaf(m.z, xr[cc + 2], a); a = fmaf(m.w, xr[cc + 3], a);
+      }
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      if (fq == 0) yl[((j + k) / CL) * NB + fr] -= (double)a;
+    }
+    __syncthreads();
+    if (j + 1 < nbr && c == (j + 1) % CL && tid < NB) {
+      const float v = (float)yl[((j + 1) / CL) * NB + tid];
+      for (int q = 0; q < CL; ++q) cluster.map_shared_rank(&xb[0][0], q)[((j + 1) & 1) * NB + tid] = v;
+    }
+    cluster.sync();
+  }
+  __pipeline_wait_prior(0);
+  // ---------------- diagonal: w_R = D_R y_R for the rows this CTA owns (FP64) ----------------
+  for (int R = c; R < nbr; R += CL) {
+    const int lr = R / CL;
+    const double* D = invd + (size_t)R * NB2 + (size_t)(bq * 16) * NB + bc;     // D symmetric: rows as columns
+    const double* yr = yl + lr * NB + bq * 16;
+    double d[16];
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) d[rr] = __ldcs(D + rr * NB);
+    double acc = 0.0;
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) acc = fma(d[rr], yr[rr], acc);
+    redd[bq][bc] = acc;
+    __syncthreads();
+    if (tid < NB) yl[lr * NB + tid] = (redd[0][tid] + redd[1][tid]) + (redd[2][tid] + redd[3][tid]);
+    __syncthreads();
+  }
+  // ---------------- backward ----------------
+  const int last = nbr - 1;
+  cc_prefetch(S.band32, offc, rlen, nbr, last, c, CL, true, ring + (last % 3) * stage_sz);
+  cc_prefetch(S.band32, offc, rlen, nbr, last - 1, c, CL, true, ring + ((last + 2) % 3) * stage_sz);
+  if (c == last % CL && tid < NB) {
+    const float v = (float)yl[(last / CL) * NB + tid];
+    for (int q = 0; q < CL; ++q) cluster.map_shared_rank(&xb[0][0], q)[(last & 1) * NB + tid] = v;
+  }
+  cluster.sync();
+  for (int j = last; j >= 0; --j) {
+    cc_prefetch(S.band32, offc, rlen, nbr, j - 2, c, CL, true, ring + ((j + 1) % 3) * stage_sz);   // (j-2) % 3 == (j+1) % 3
+    __pipeline_wait_prior(2);
+    __syncthreads();
+    float xr[16];
+#pragma unroll
+    for (int cc = 0; cc < 16; cc += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(&xb[j & 1][bq * 16 + cc]);
+      xr[cc] = v.x; xr[cc + 1] = v.y; xr[cc + 2] = v.z; xr[cc + 3] = v.w;
+    }
+    const float* stage = ring + (j % 3) * stage_sz;
+    const int kmax = rlen[j];
+    int t = 0;
+    for (int k = cc_k0(c, j, CL, true); k <= kmax; k += CL, ++t) {
+      const float* p = stage + t * PBLK + (bq * 16) * LDS + bc;
+      float a = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) a = fmaf(p[rr * LDS], xr[rr], a);
+      redc[bq][bc] = a;
+      __syncthreads();
+      if (tid < NB) yl[((j - k) / CL) * NB + tid] -= (double)((redc[0][tid] + redc[1][tid]) + (redc[2][tid] + redc[3][tid]));
+      __syncthreads();
+    }
+    if (j >= 1 && c == (j - 1) % CL && tid < NB) {
+      const float v = (float)yl[((j - 1) / CL) * NB + tid];
+      for (int q = 0; q < CL; ++q) cluster.map_shared_rank(&xb[0][0], q)[((j - 1) & 1) * NB + tid] = v;
+    }
+    cluster.sync();
+  }
+  __pipeline_wait_prior(0);
+  for (int idx = tid; idx < rows_loc * NB; idx += 256) {
+    const int R = (idx / NB) * CL + c;
+    if (R < nbr) y[(size_t)R * NB + (idx % NB)] = yl[idx];
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_dot_slot0(int64_t n, const double* x, const double* y, double* partial2) {
   __shared__ double sh[32];
@@ -684,6 +852,48 @@ static int sw1_caps(int max_n_pad, bool with_coarse, size_t* smem_out) {
   return cap;
 }
 
+// Coarse block on one thread-block cluster (16 CTAs, else 8).  Returns 1 when launched, 0 when the
+// block does not fit (caller falls back to the barrier-group kernel), <0 on a launch error.
+static int launch_coarse_cluster(const GfSchwarz* Sc, cudaStream_t st) {
+  static int CL = -1;                            // cluster size found usable on this device (0: none)
+  static size_t smem_set = 0;
+  const int tries[2] = {16, 8};
+  for (int a = 0; a < 2; ++a) {
+    const int cl = (CL > 0) ? CL : tries[a];
+    if (CL == 0) return 0;
+    const int TPS = (Sc->max_mb + cl - 1) / cl > 0 ? (Sc->max_mb + cl - 1) / cl : 1;
+    const int rows_loc = (Sc->max_nbr + cl - 1) / cl;
+    const size_t smem = (size_t)3 * TPS * PBLK * sizeof(float) + (size_t)rows_loc * NB * sizeof(double) + (size_t)Sc->max_nbr * 16;
+    bool ok = smem <= 200 * 1024;
+    if (ok && cl > 8 && CL < 0) ok = cudaFuncSetAttribute(k_sw_coarse_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (ok && smem > smem_set) {
+      ok = cudaFuncSetAttribute(k_sw_coarse_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+      if (ok) smem_set = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cl); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (ok && CL < 0) {
+      int ncl = 0;
+      ok = cudaOccupancyMaxActiveClusters(&ncl, k_sw_coarse_cluster, &cfg) == cudaSuccess && ncl >= 1;
+    }
+    if (ok) {
+      cudaError_t e = cudaLaunchKernelEx(&cfg, k_sw_coarse_cluster, *Sc, TPS);
+      if (e != cudaSuccess) { set_cuda_error(e, "launch k_sw_coarse_cluster"); return -1; }
+      CL = cl;
+      count_launch(1);
+      return 1;
+    }
+    cudaGetLastError();
+    if (CL > 0) return 0;                        // this coarse block is too large for the known cluster size
+  }
+  CL = 0;
+  return 0;
+}
+
 // z_f = sum_i R_i^T A_i^-1 R_i r_f  (fine blocks of Sf)  and, if Sc != NULL, z_c = Kc^-1 r_c
 // (single block of Sc) with both sets of triangular sweeps running concurrently.
 extern "C" int gf_schwarz_apply2(const GfSchwarz* Sf, const double* r_f, double* z_f, int64_t n_f,
@@ -701,35 +911,65 @@ extern "C" int gf_schwarz_apply2(const GfSchwarz* Sf, const double* r_f, double*
   if (Sfv.debug_flags & 4) mode = 1;
   if (Sfv.debug_flags & 8) mode = 0;
   int G_c = 0;
+  bool coarse_side = false;                       // coarse sweeps on their own stream, concurrent with the fine ones
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t sf = st;                           // stream of the fine sweeps
   if (Sc) {
     int gc = (int)((Sc->n_y + 255) / 256); if (gc > 2048) gc = 2048;
     k_sw_gather_in<<<gc, 256, 0, st>>>(*Sc, r_c);
-    e = cudaMemsetAsync(Sc->barrier, 0, sizeof(unsigned) * Sc->nblocks, st);
-    if (e != cudaSuccess) return set_cuda_error(e, "gf_schwarz_apply memset");
     count_launch(1);
-    G_c = cap / 6; if (G_c > Sc->max_mb) G_c = Sc->max_mb; if (G_c < 1) G_c = 1;
+    if (mode && !(Sfv.debug_flags & 16)) {
+      if (!side) {
+        if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)
+          return set_error(GF_ERR_CUDA, "gf_schwarz_apply: cannot create the second sweep stream");
+      }
+      // The cluster needs 16 SMs of ONE GPC with room for it, which the fine CTAs would not leave:
+      // it goes first, on the caller's stream; the fine sweeps follow on a second stream (behind an
+      // event recorded before the cluster launch) and fill the rest of the machine around it.
+      e = cudaEventRecord(ev_fork, st);
+      if (e != cudaSuccess) return set_cuda_error(e, "gf_schwarz_apply fork");
+      const int lc = launch_coarse_cluster(Sc, st);
+      if (lc < 0) return GF_ERR_CUDA;
+      if (lc == 1) {
+        int g3 = (int)((n_c + 255) / 256); if (g3 > 2048) g3 = 2048;
+        k_sw_gather_out<<<g3, 256, 0, st>>>(*Sc, z_c, n_c);
+        count_launch(1);
+        e = cudaStreamWaitEvent(side, ev_fork, 0);
+        if (e != cudaSuccess) return set_cuda_error(e, "gf_schwarz_apply fork");
+        coarse_side = true;
+        sf = side;
+      }
+    }
+    if (!coarse_side) {
+      e = cudaMemsetAsync(Sc->barrier, 0, sizeof(unsigned) * Sc->nblocks, st);
+      if (e != cudaSuccess) return set_cuda_error(e, "gf_schwarz_apply memset");
+      G_c = cap / 6; if (G_c > Sc->max_mb) G_c = Sc->max_mb; if (G_c < 1) G_c = 1;
+    }
   }
   // one CTA per block whenever a block's vector fits in shared memory (otherwise: G CTAs per block)
   size_t smem1 = 0;
   int cap1 = 0;
-  if (mode && Sf->max_mb < XW) cap1 = sw1_caps(Sf->max_n_pad, Sc != nullptr, &smem1);
+  if (mode && Sf->max_mb < XW) cap1 = sw1_caps(Sf->max_n_pad, Sc != nullptr && !coarse_side, &smem1);
   if (cap1 > G_c) {
-    for (int b0 = 0; b0 < Sf->nblocks;) {
+    for (int b0 = (Sfv.debug_flags & 32) ? Sf->nblocks : 0; b0 < Sf->nblocks;) {   // 32: timing experiments, coarse only
       const int gcl = (b0 == 0) ? G_c : 0;       // the coarse group rides along with the first batch
       int nb_l = Sf->nblocks - b0;
       if (nb_l > cap1 - gcl) nb_l = cap1 - gcl;
       int first = b0;
       void* args[] = {&Sfv, &r_f, &first, &Scv, (void*)&gcl};
-      if (gcl) e = cudaLaunchCooperativeKernel((void*)k_sw_solve1, dim3(nb_l + gcl), dim3(256), args, smem1, st);
-      else { k_sw_solve1<<<nb_l, 256, smem1, st>>>(Sfv, r_f, first, Scv, 0); e = cudaGetLastError(); }
+      if (gcl) e = cudaLaunchCooperativeKernel((void*)k_sw_solve1, dim3(nb_l + gcl), dim3(256), args, smem1, sf);
+      else { k_sw_solve1<<<nb_l, 256, smem1, sf>>>(Sfv, r_f, first, Scv, 0); e = cudaGetLastError(); }
       if (e != cudaSuccess) return set_cuda_error(e, "launch k_sw_solve1");
       count_launch(1);
       b0 += nb_l;
     }
   } else {
     int g = (int)((Sf->n_y + 255) / 256); if (g > 2048) g = 2048;
-    k_sw_gather_in<<<g, 256, 0, st>>>(*Sf, r_f);
-    e = cudaMemsetAsync(Sf->barrier, 0, sizeof(unsigned) * Sf->nblocks, st);
+    k_sw_gather_in<<<g, 256, 0, sf>>>(*Sf, r_f);
+    e = cudaMemsetAsync(Sf->barrier, 0, sizeof(unsigned) * Sf->nblocks, sf);
     if (e != cudaSuccess) return set_cuda_error(e, "gf_schwarz_apply memset");
     count_launch(1);
     int G = (cap - G_c) / Sf->nblocks;
@@ -741,17 +981,22 @@ extern "C" int gf_schwarz_apply2(const GfSchwarz* Sf, const double* r_f, double*
       int first = b0;
       int gcl = (b0 == 0) ? G_c : 0;               // the coarse block rides along with the first batch
       void* args[] = {&Sfv, &G, &first, &nb_l, &Scv, &gcl};
-      e = cudaLaunchCooperativeKernel((void*)k_sw_solve, dim3(nb_l * G + gcl), dim3(256), args, PF * PBLK * sizeof(float), st);
+      e = cudaLaunchCooperativeKernel((void*)k_sw_solve, dim3(nb_l * G + gcl), dim3(256), args, PF * PBLK * sizeof(float), sf);
       if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchCooperativeKernel(k_sw_solve)");
       count_launch(1);
     }
   }
   int g2 = (int)((n_f + 255) / 256); if (g2 > 2048) g2 = 2048;
-  k_sw_gather_out<<<g2, 256, 0, st>>>(*Sf, z_f, n_f);
-  if (Sc) {
+  k_sw_gather_out<<<g2, 256, 0, sf>>>(*Sf, z_f, n_f);
+  if (Sc && !coarse_side) {
     int g3 = (int)((n_c + 255) / 256); if (g3 > 2048) g3 = 2048;
     k_sw_gather_out<<<g3, 256, 0, st>>>(*Sc, z_c, n_c);
     count_launch(1);
+  }
+  if (coarse_side) {
+    e = cudaEventRecord(ev_join, side);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev_join, 0);
+    if (e != cudaSuccess) return set_cuda_error(e, "gf_schwarz_apply join");
   }
   count_launch(1);
   return check_launch("gf_schwarz_apply");

@@ -183,7 +183,9 @@ typedef struct GfSchwarz {
   int32_t nblocks, nb;            /* nb = 64                                          */
   int32_t max_nbr, max_mb, max_n_pad;
   int32_t debug_flags;            /* 0 in production; timing experiments: 1 skip block GEMVs, 2 skip barriers;
-                                     sweep kernel choice: 4 = one CTA per block, 8 = CTA group per block (default: by block count) */
+                                     sweep kernel choice: 4 = one CTA per block, 8 = CTA group per block,
+                                     16 = no thread-block cluster for the coarse block (default: single CTA + cluster when they fit);
+                                     32 = timing experiments: skip the fine sweeps */
   int64_t n_y, band_len;          /* total padded local dofs; band storage length     */
   const int32_t* n_pad;           /* [nblocks] padded local size (multiple of nb)     */
   const int32_t* nbr;             /* [nblocks] block rows                             */

@@ -32,6 +32,16 @@ for _ in range(20):
     dm.precond_apply(b, z)
 ev[1].record(); torch.cuda.synchronize()
 pc_ms = ev[0].elapsed_time(ev[1]) / 20
+coarse_only_ms = None
+if mode == "single" and dm.coarse_nc > 0:
+    dm._schwarz().debug_flags = 4 | 32          # timing only: coarse sweeps without the fine ones
+    dm.precond_apply(b, z)
+    ev[0].record()
+    for _ in range(20):
+        dm.precond_apply(b, z)
+    ev[1].record(); torch.cuda.synchronize()
+    coarse_only_ms = ev[0].elapsed_time(ev[1]) / 20
+    dm.set_sweep_mode(mode)
 ev[0].record()
 dm.factor_preconditioner()
 ev[1].record(); torch.cuda.synchronize()
@@ -42,6 +52,6 @@ x = dm.solve(b)
 ev[1].record(); torch.cuda.synchronize()
 print(json.dumps({"n_el": n_el, "N": dm.sym.N, "mode": mode, "sub": sub, "layers": layers, "coarse_nc": dm.coarse_nc, "blocks": A["nblocks"],
                   "band32_GB": A["band_len"] * 4 / 1e9, "max_n_pad": A["max_n_pad"], "max_mb": A["max_mb"],
-                  "precond_ms": pc_ms, "factor_ms": fac_ms, "pcg_its": dm.last_krylov_its,
+                  "precond_ms": pc_ms, "precond_coarse_only_ms": coarse_only_ms, "factor_ms": fac_ms, "pcg_its": dm.last_krylov_its,
                   "solve_ms": ev[0].elapsed_time(ev[1]), "relres": dm.last_relres, "setup_s": t_setup,
                   "x_norm": float(x.norm())}), flush=True)

@@ -1,6 +1,7 @@
-"""GPU: the two triangular-sweep kernels of the Schwarz preconditioner (one CTA per block with the
-vector in shared memory / a CTA group per block with a global-memory barrier) apply the same
-operator: same CG iteration counts, same solution, and that solution is the LU one."""
+"""GPU: the triangular-sweep kernels of the Schwarz preconditioner (fine blocks: one CTA per block with
+the vector in shared memory / a CTA group per block with a global-memory barrier; coarse block: one
+thread-block cluster / a barrier group) apply the same operator: same CG iteration counts, same
+solution, and that solution is the LU one."""
 import numpy as np
 import pytest
 import scipy.sparse.linalg as spla
@@ -28,7 +29,7 @@ def test_sweep_kernels_agree(built_lib, sub):
     r = torch.from_numpy(rng.standard_normal(dm.sym.N)).to(dm.device)
     r[torch.from_numpy(np.asarray(dm.sym.bc_list)).to(dm.device).long()] = 0.0
     out = {}
-    for mode in ("group", "single"):
+    for mode in ("group", "single_nocluster", "single"):
         dm.set_sweep_mode(mode)
         z = dm.precond_apply(r).cpu().numpy().copy()
         z2 = dm.precond_apply(r).cpu().numpy().copy()
@@ -37,9 +38,10 @@ def test_sweep_kernels_agree(built_lib, sub):
         out[mode] = (z, x, dm.last_krylov_its)
     torch.cuda.synchronize()
     zg, xg, ig = out["group"]
-    zs, xs, i_s = out["single"]
-    assert np.isfinite(zs).all() and rel(zs, zg) < 1e-3      # FP32 panel products, different summation order
-    assert abs(ig - i_s) <= 3
-    assert rel(xs, xg) < 1e-8
+    for mode in ("single_nocluster", "single"):
+        zs, xs, i_s = out[mode]
+        assert np.isfinite(zs).all() and rel(zs, zg) < 1e-3      # FP32 panel products, different summation order
+        assert abs(ig - i_s) <= 5                                # convergence is checked every 5 iterations
+        assert rel(xs, xg) < 1e-8
     xe = spla.splu(dm.K.to_scipy().tocsc()).solve(b.cpu().numpy())
     assert rel(xs, xe) < 1e-6
