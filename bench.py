@@ -108,6 +108,9 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- our arm
+SWEEP_TRAFFIC_C3 = 7182546432      # dram read 7170125056 + write 12421376 B of one k_sw_solve1 launch at n_el = 201 (profiles/r1_ncu_sweeps_c3.txt)
+
+
 class Step:
     """One analysis+adjoint iteration on the device model (inputs resident in HBM)."""
 
@@ -336,6 +339,17 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    # ---- roofline of the kernel with the largest share of the step: the fine Schwarz sweeps (k_sw_solve1) ----
+    # algorithmic bytes per launch = every solve-form panel tile (FP32) once forward and once backward, the
+    # diagonal blocks D_j (FP64) once, the block-local vector in (index + gathered value) and out
+    import ctypes as C
+    from goldfish_b200 import _capi as capi
+    sw = dm._schwarz(); A = dm._sw[3]
+    sweep_bytes = 2 * int(A["mbj"].sum()) * 64 * 64 * 4 + int(A["nbr"].sum()) * 64 * 64 * 8 + int(A["n_y"]) * (4 + 8 + 8)
+    rsw = dm.R.clone()
+    sweep_ms = time_kernel(torch, lambda: capi.check(dm.lib.gf_schwarz_sweeps(C.byref(sw), C.c_void_p(rsw.data_ptr()), dm._stream()),
+                                                     "gf_schwarz_sweeps"), 20, flush)
+    sweep_gbs = sweep_bytes / (sweep_ms * 1e-3) / 1e9
     # assembly kernels (FP64-pipe bound; reported beside the roofline object)
     asm_ms = time_kernel(torch, lambda: dm.assemble(tangent=True, residual=True), 5, flush)
     nq = S.nq
@@ -347,7 +361,7 @@ def main():
             phases[timers[i][0]] = phases.get(timers[i][0], 0.0) + timers[i - 1][1].elapsed_time(timers[i][1]) / len(step_timers)
     phases = {k: round(v, 2) for k, v in phases.items()}
     fac_ms = time_kernel(torch, lambda: dm.factor_preconditioner(), 2, flush)
-    kernels = {"phase_ms": phases, "precond_factor_ms": fac_ms, "spmv_ms": spmv_ms, "spmv_gbs": achieved,
+    kernels = {"phase_ms": phases, "precond_factor_ms": fac_ms, "spmv_ms": spmv_ms, "spmv_gbs": achieved, "sweeps_ms": sweep_ms, "sweeps_gbs": sweep_gbs,
                "assemble_RK_ms": asm_ms, "assemble_RK_material_tflops": asm_flops / (asm_ms * 1e-3) / 1e12,
                "assemble_RK_gbs_algorithmic": (8 * dm.K.nnz + 8 * (4 * S.n_scalar + S.N + S.n_th)) / (asm_ms * 1e-3) / 1e9,
                "newton_its": step.info.get("newton_its"), "krylov_its": step.info.get("krylov_its")}
@@ -363,13 +377,19 @@ def main():
                            "parallelism": "1 GPU" if world == 1 else "patch-sharded over %d GPUs (rows + Schwarz blocks owned, vectors replicated, NCCL all-reduce)" % world},
                 "e2e": {"value": args.steps / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "k_spmv", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak,
-                             # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_spmv launch on this workload
-                             # (ncu --set full, profiles/r1_ncu_spmv_c3.txt); algorithmic bytes are spmv_bytes
-                             "traffic": 1887203640 if (args.n_el == 201 and world == 1) else None,
-                             "algorithmic_bytes": int(spmv_bytes),
+                "roofline": {"bound": "hbm", "kernel": "k_sw_solve1", "achieved": sweep_gbs, "peak": peak, "unit": "GB/s",
+                             "frac": sweep_gbs / peak,
+                             # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_sw_solve1 launch on this workload
+                             # (ncu --set full, profiles/r1_ncu_sweeps_c3.txt)
+                             "traffic": SWEEP_TRAFFIC_C3 if (args.n_el == 201 and world == 1) else None,
+                             "algorithmic_bytes": int(sweep_bytes), "launch_ms": sweep_ms,
+                             "launches_per_step": int(sum(step.info.get("krylov_its") or []) + len(step.info.get("krylov_its") or [])),
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"},
+                "roofline_spmv": {"bound": "hbm", "kernel": "k_spmv", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                                  "frac": achieved / peak,
+                                  # ncu --set full of ONE k_spmv launch on this workload (profiles/r1_ncu_spmv_c3.txt)
+                                  "traffic": 1887203640 if (args.n_el == 201 and world == 1) else None,
+                                  "algorithmic_bytes": int(spmv_bytes)},
                 "kernels": kernels, "clocks": cs.summary()}
         if world == 1:
             line["other_configs"] = small_configs(torch)

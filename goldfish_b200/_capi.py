@@ -112,6 +112,7 @@ SIGNATURES = {
     "gf_schwarz_apply": [C.POINTER(GfSchwarz), c_vp, c_vp, c_i64, c_vp],
     "gf_schwarz_apply2": [C.POINTER(GfSchwarz), c_vp, c_vp, c_i64, C.POINTER(GfSchwarz), c_vp, c_vp, c_i64, c_vp],
     "gf_dot_slot0": [c_i64, c_vp, c_vp, c_vp, C.c_int, c_vp],
+    "gf_schwarz_sweeps": [C.POINTER(GfSchwarz), c_vp, c_vp],
     "gf_precond_apply": [C.POINTER(GfPrecond), c_vp, c_vp, c_i64, c_vp],
     "gf_jacobi_setup": [C.POINTER(GfCsr), c_vp, c_vp],
     "gf_axpby": [c_i64, c_f64, c_vp, c_f64, c_vp, c_vp],

@@ -1002,6 +1002,20 @@ extern "C" int gf_schwarz_apply2(const GfSchwarz* Sf, const double* r_f, double*
   return check_launch("gf_schwarz_apply");
 }
 
+// Fine sweeps alone (one CTA per block), result left in S->y: the launch bench.py times for the roofline.
+extern "C" int gf_schwarz_sweeps(const GfSchwarz* S, const double* r, void* stream) {
+  if (!S || !r) return set_error(GF_ERR_BADARG, "gf_schwarz_sweeps: null argument");
+  size_t smem1 = 0;
+  const int cap1 = (S->max_mb < XW) ? sw1_caps(S->max_n_pad, false, &smem1) : 0;
+  if (cap1 < 1) return set_error(GF_ERR_BADARG, "gf_schwarz_sweeps: blocks do not fit the one-CTA-per-block kernel");
+  for (int b0 = 0; b0 < S->nblocks; b0 += cap1) {
+    const int nb_l = (S->nblocks - b0 < cap1) ? S->nblocks - b0 : cap1;
+    k_sw_solve1<<<nb_l, 256, smem1, (cudaStream_t)stream>>>(*S, r, b0, *S, 0);
+    count_launch(1);
+  }
+  return check_launch("k_sw_solve1");
+}
+
 extern "C" int gf_schwarz_apply(const GfSchwarz* S, const double* r, double* z, int64_t n, void* stream) {
   return gf_schwarz_apply2(S, r, z, n, nullptr, nullptr, nullptr, 0, stream);
 }

@@ -217,6 +217,8 @@ int gf_schwarz_apply(const GfSchwarz* s, const double* r, double* z, int64_t n, 
  * gathered by the kernel); otherwise a group of CTAs shares each block through a global-memory barrier. */
 int gf_schwarz_apply2(const GfSchwarz* fine, const double* r_f, double* z_f, int64_t n_f,
                       const GfSchwarz* coarse, const double* r_c, double* z_c, int64_t n_c, void* stream);
+/* the fine triangular sweeps alone (k_sw_solve1, one CTA per block); result stays in s->y (bench.py roofline) */
+int gf_schwarz_sweeps(const GfSchwarz* s, const double* r, void* stream);
 int gf_dot_slot0(int64_t n, const double* x, const double* y, double* partial2, int grid, void* stream);
 
 /* Two-level preconditioner  z = sum_i R_i^T A_i^-1 R_i r  +  P Kc^-1 P^T r :
