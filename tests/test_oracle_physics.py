@@ -27,6 +27,46 @@ def test_scordelis_lo_known_answer():
     assert abs(-uy - q["ref"]) < 2e-3 * q["ref"]
 
 
+def _flat_patch_problem(a, b, n0, n1, bc, E, nu, t, body_force=(0.0, 0.0, 0.0), edge_loads=()):
+    from goldfish_b200.problems import _ruled_quad, _patch_from_surface
+    srf = _ruled_quad([[0, 0, 0], [a, 0, 0], [0, b, 0], [a, b, 0]], n0, n1, 3)
+    P = _patch_from_surface(srf, 9, dict(kind="const", values=t), bc, body_force)
+    return dict(name="flat", patches=[P], E=E, nu=nu, interfaces=[], penalty_coefficient=1e3, point_loads=[],
+                edge_loads=list(edge_loads))
+
+
+def _probe(m, u, xi, field):
+    P = m.patches[0]
+    conn, D = obs.surface_basis(P.ku, P.kv, 3, 3, P.cp[:, 3], np.array([xi]))
+    return float((D[0, 0] * u[P.off + field * P.ncp + conn[0]]).sum())
+
+
+def test_navier_plate_known_answer():
+    """Simply supported square plate under uniform load, nu = 0.3: w_max = 0.00406235 q a^4 / D with
+    D = E t^3 / (12 (1 - nu^2)) (Timoshenko & Woinowsky-Krieger, table 8).  Anchors the bending stiffness
+    and its nu dependence, which Scordelis-Lo and the T-beam (both nu = 0) do not see."""
+    E, nu, t, a, q = 1.0e7, 0.3, 0.01, 1.0, 1.0e-3
+    bc = [(f, d, s, 1) for f in range(3) for d in (0, 1) for s in (0, 1)]
+    m = OracleModel(_flat_patch_problem(a, a, 8, 8, bc, E, nu, t, body_force=(0.0, 0.0, q)))
+    w = _probe(m, m.solve_linear(), (0.5, 0.5), 2)
+    ref = 0.00406235 * q * a ** 4 / (E * t ** 3 / (12 * (1 - nu ** 2)))
+    assert abs(w - ref) < 2e-4 * ref
+
+
+def test_uniaxial_tension_poisson_contraction():
+    """Strip under an edge traction N (force per unit length): u_x = N x / (E t), u_y = -nu N y / (E t)
+    exactly (the state is in the spline space): membrane stiffness and Poisson coupling."""
+    E, nu, t, L, W, N = 1.0e7, 0.3, 0.01, 2.0, 1.0, 5.0
+    bc = [(0, 0, 0, 1), (1, 1, 0, 1), (2, 0, 0, 2)]
+    pr = _flat_patch_problem(L, W, 4, 3, bc, E, nu, t,
+                             edge_loads=[dict(patch=0, direction=0, side=1, traction=(N, 0.0, 0.0))])
+    m = OracleModel(pr)
+    u = m.solve_linear()
+    assert abs(_probe(m, u, (1.0, 1.0), 0) - N * L / (E * t)) < 1e-10 * N * L / (E * t)
+    assert abs(_probe(m, u, (1.0, 1.0), 1) + nu * N * W / (E * t)) < 1e-10 * N * W / (E * t)
+    assert abs(_probe(m, u, (0.5, 0.5), 0) - 0.5 * N * L / (E * t)) < 1e-10 * N * L / (E * t)
+
+
 def test_tangent_symmetric_and_fd(tb):
     m = tb
     K = m.stiffness(apply_bcs=False)
