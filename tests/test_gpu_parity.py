@@ -203,3 +203,25 @@ def test_patch_sharded_two_gpus_match_single_gpu():
     assert max(res["u"], res["lam"], res["gT"], res["gP"]) < 1e-7
     # same preconditioner, all-reduce changes the summation order: counts agree up to the check interval
     assert all(abs(a - b) <= 10 for a, b in zip(res["its_sharded"], res["its_single"]))
+
+
+def test_pinched_ring_known_answer_on_gpu(DM):
+    """The CUDA path against a closed-form answer (not the oracle): ring of four 90-degree NURBS patches under two
+    opposite radial loads, decrease of the loaded diameter = (pi/4 - 2/pi) P R^3 / (E I)."""
+    import test_cpu_port as T
+    from oracle import bspline as obs
+    R, b, t, E, F = 1.0, 0.1, 0.01, 1.0e7, 1.0e-3
+    pr = T._free_cylinder(12, R, b, t, E, 0.0, False, 1)
+    pr["point_loads"] = [dict(patch=0, field=1, xi=(1.0, 0.5), value=+F), dict(patch=2, field=1, xi=(1.0, 0.5), value=-F)]
+    dm = DM(pr)
+    dm.set_u(np.zeros(dm.sym.N))
+    dm.assemble(residual=True, tangent=True)
+    u = dm.solve(-dm.R.clone(), refactor=True, max_it=5000).cpu().numpy()
+    om = OracleModel(pr)
+    d = 0.0
+    for s, sg in ((0, 1.0), (2, -1.0)):
+        P = om.patches[s]
+        conn, D = obs.surface_basis(P.ku, P.kv, 3, 3, P.cp[:, 3], np.array([(1.0, 0.5)]))
+        d -= sg * (D[0, 0] * u[P.off + P.ncp + conn[0]]).sum()
+    ref = (np.pi / 4 - 2 / np.pi) * F * R ** 3 / (E * b * t ** 3 / 12)
+    assert abs(d / ref - 1.0) < 2e-3
