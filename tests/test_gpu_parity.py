@@ -225,3 +225,28 @@ def test_pinched_ring_known_answer_on_gpu(DM):
         d -= sg * (D[0, 0] * u[P.off + P.ncp + conn[0]]).sum()
     ref = (np.pi / 4 - 2 / np.pi) * F * R ** 3 / (E * b * t ** 3 / 12)
     assert abs(d / ref - 1.0) < 2e-3
+
+
+def test_pinched_free_cylinder_known_answer_on_gpu(DM):
+    """Shell obstacle course through the CUDA path: pinched cylinder with free ends on eight NON-MATCHING NURBS
+    patches (nu = 0.3125), radial displacement under the loads 0.1139 (two-level Schwarz PCG solve)."""
+    import test_cpu_port as T
+    from oracle import bspline as obs
+    R, L, t, E, nu, F = 4.953, 10.35, 0.094, 10.5e6, 0.3125, 100.0
+    pr = T._free_cylinder(12, R, L, t, E, nu, True, 2)
+    c = np.sqrt(0.5) * F / T.W_MID                      # point sources act on the homogeneous basis (see test_cpu_port)
+    pr["point_loads"] = [dict(patch=0, field=0, xi=(0.5, 1.0), value=+c), dict(patch=0, field=1, xi=(0.5, 1.0), value=+c),
+                         dict(patch=2, field=0, xi=(0.5, 1.0), value=-c), dict(patch=2, field=1, xi=(0.5, 1.0), value=-c)]
+    dm = DM(pr)
+    dm.set_u(np.zeros(dm.sym.N))
+    dm.assemble(residual=True, tangent=True)
+    u = dm.solve(-dm.R.clone(), refactor=True, max_it=5000).cpu().numpy()
+    om = OracleModel(pr)
+    s = np.sqrt(0.5)
+    w = 0.0
+    for k, sg in ((0, 1.0), (2, -1.0)):
+        P = om.patches[k]
+        conn, D = obs.surface_basis(P.ku, P.kv, 3, 3, P.cp[:, 3], np.array([(0.5, 1.0)]))
+        w -= 0.5 * sg * s * sum((D[0, 0] * u[P.off + f * P.ncp + conn[0]]).sum() for f in range(2))
+    assert abs(w / 0.1139 - 1.0) < 1.5e-2
+    assert abs(w - 0.11284133200040206) < 1e-7 * w      # the compiled CPU port's value on the same mesh
