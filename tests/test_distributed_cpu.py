@@ -71,3 +71,81 @@ def test_lpt_is_balanced_and_deterministic():
     assert ptr.tolist() == [0, 2, 5] and items.tolist() == [0, 1, 2, 3, 4]
     ptr, items = filter_ragged(np.array([0, 2, 2, 5]), np.arange(5), np.array([False, True, False]))
     assert ptr.tolist() == [0, 0] and len(items) == 0
+
+
+def _pcg_worker(rank, world, port, q):
+    """The exchange steps of the sharded Krylov solve, emulated with scipy over gloo:
+    each rank multiplies its OWN rows and solves its OWN Schwarz blocks, both results are summed with an
+    all-reduce, every rank then holds identical full vectors and computes the dot products redundantly."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import scipy.sparse.linalg as spla
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from goldfish_b200 import problems, _capi as capi
+    from goldfish_b200.partition import lpt_partition, shard_symbolic
+    from goldfish_b200.schwarz import SchwarzSetup
+    from oracle.cpu_port import CpuModel
+    pr = problems.cylinder(n_el=6)
+    cm = CpuModel(pr)
+    S = cm.S
+    cm.set_u(np.zeros(S.N))
+    cm.shell(capi.GF_OUT_R | capi.GF_OUT_K)
+    K = cm.K_matrix().tocsr(); b = -cm.residual()
+    owner = lpt_partition([P.nel for P in S.patches], world)
+    sh = shard_symbolic(S, owner, rank)
+    own = np.zeros(S.N, dtype=bool)
+    for b0, b1 in sh["own_ranges"]:
+        own[b0:b1] = True
+    K_own = K[np.nonzero(own)[0]]
+    SW = SchwarzSetup(S, layers=2, sub=8)
+    n_all = len(SW.blocks)
+    SW.keep_blocks([owner[bl["patch"]] == rank for bl in SW.blocks])
+    lus = []
+    for bl in SW.blocks:
+        g = bl["glob"][bl["glob"] >= 0]
+        lus.append((g, spla.splu(K[g][:, g].tocsc())))
+
+    def allreduce(v):
+        t = torch.from_numpy(v); dist.all_reduce(t); return t.numpy()
+
+    def matvec(p):
+        y = np.zeros(S.N); y[own] = K_own @ p
+        return allreduce(y)
+
+    def precond(r):
+        z = np.zeros(S.N)
+        for g, lu in lus:
+            z[g] += lu.solve(r[g])
+        return allreduce(z)
+
+    x = np.zeros(S.N); r = b.copy(); z = precond(r); p = z.copy(); rz = r @ z; bn = np.linalg.norm(b); its = 0
+    for its in range(1, 401):
+        Ap = matvec(p); a = rz / (p @ Ap); x += a * p; r -= a * Ap
+        if np.linalg.norm(r) < 1e-10 * bn:
+            break
+        z = precond(r); rz2 = r @ z; p = z + (rz2 / rz) * p; rz = rz2
+    counts = [None] * world
+    dist.all_gather_object(counts, (its, len(SW.blocks), float(np.linalg.norm(x))))
+    if rank == 0:
+        xe = spla.splu(K.tocsc()).solve(b)
+        ok = (np.linalg.norm(x - xe) < 1e-6 * np.linalg.norm(xe)                 # the sharded solve is the LU solution
+              and len({c[0] for c in counts}) == 1 and len({c[2] for c in counts}) == 1   # identical on every rank
+              and sum(c[1] for c in counts) == n_all and its < 200)               # every block solved exactly once
+        q.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_krylov_exchange_over_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_pcg_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
