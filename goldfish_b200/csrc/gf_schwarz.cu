@@ -7,14 +7,16 @@
 // patch block overlap the neighbouring patches by a few control-point layers
 // puts each spring inside a block; CG then needs tens of iterations.
 //
-// One block per patch:  nodes = patch CPs + overlap layers, ordered so that the
-// block matrix is banded (host: goldfish_b200/schwarz.py); 3 dofs per node
-// interleaved.  The band is stored as dense nb x nb blocks, block column j
-// holding blocks (j+k, j), k = 0..mb.
-//   factor : right-looking block Cholesky, 3 kernels per block column,
-//            all patch blocks batched in gridDim.y
-//   solve  : ONE cooperative kernel, G CTAs per patch block walk the block
-//            columns with a per-group global-memory barrier per step
+// One block per sub-domain (a rectangle of a patch's control net):  nodes = own CPs + overlap layers,
+// ordered so that the block matrix is banded (host: goldfish_b200/schwarz.py); 3 dofs per node
+// interleaved.  The band is stored as dense nb x nb blocks, block column j holding blocks (j+k, j),
+// k = 0..mb_j.
+//   factor : right-looking block Cholesky, 3 kernels per block column, all blocks batched in gridDim.y,
+//            then "solve form"  M(j+k,j) = L(j+k,j) L_jj^-1,  D_j = (L_jj L_jj^T)^-1  (+ FP32 copy of M)
+//   solve  : k_sw_solve1          one CTA per fine block, block vector in shared memory (HBM-bound stream)
+//            k_sw_coarse_cluster  the single coarse block on a 16-CTA thread-block cluster (DSMEM broadcast),
+//                                 concurrent with the fine sweeps
+//            k_sw_solve           fallback: G CTAs per block with a per-group global-memory barrier per step
 //   z = sum_i R_i^T (L_i L_i^T)^-1 R_i r  assembled by a fixed-order gather.
 #include "gf_common.cuh"
 #include <stdlib.h>
