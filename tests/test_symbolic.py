@@ -54,3 +54,29 @@ def test_empty_and_ragged_inputs():
     pr2["patches"][0]["p"] = (2, 3)
     with pytest.raises(ValueError):
         Symbolic(pr2)
+
+
+@pytest.mark.parametrize("case", ["slr_small", "plate_c1"])
+def test_field_rows_of_a_control_point_share_one_column_list(case):
+    """Row layout the kernels rely on: the three field rows of a control point hold the SAME
+    column list, made of groups [field 0 | field 1 | field 2] over one CP list (own stencil, then one group per
+    coupled patch).  This is what lets the scatter compute positions arithmetically, and what a node-wise SpMV
+    (one index read per three rows) will use."""
+    pr, kw = getattr(cases, case)()
+    S = Symbolic(pr, **kw)
+    ip, ix = S.K_indptr, S.K_indices
+    for P in S.patches:
+        r0 = P.dof_off + np.arange(P.ncp)
+        for i in (1, 2):
+            ri = r0 + i * P.ncp
+            assert np.array_equal(ip[ri + 1] - ip[ri], ip[r0 + 1] - ip[r0])
+        for a in range(0, P.ncp, max(1, P.ncp // 64)):                    # sample of control points
+            c0 = ix[ip[r0[a]]:ip[r0[a] + 1]]
+            for i in (1, 2):
+                r = r0[a] + i * P.ncp
+                assert np.array_equal(ix[ip[r]:ip[r + 1]], c0)
+            # own-stencil group: three consecutive blocks over the same CP list, shifted by ncp
+            nl, Sa = int(S.row_nlow[P.cp_off + a]), int(S.S_all[P.cp_off + a])
+            own = c0[nl:nl + 3 * Sa].reshape(3, Sa)
+            assert np.array_equal(own[1], own[0] + P.ncp) and np.array_equal(own[2], own[0] + 2 * P.ncp)
+            assert own[0].min() >= P.dof_off and own[0].max() < P.dof_off + P.ncp
