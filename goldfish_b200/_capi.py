@@ -95,6 +95,23 @@ class GfPcgWork(C.Structure):
                 ("scal", c_vp), ("partial", c_vp), ("scal_h", c_vp)]
 
 
+# (struct, last field) in the order of gf_abi_layout's ids
+ABI_STRUCTS = [(GfPatchDesc, "f"), (GfCsr, "vals"), (GfModel, "T"), (GfShellOut, "dt_el"), (GfPenalty, "K_pos"),
+               (GfPenaltyP, "field"), (GfCsrT, "perm"), (GfSchwarz, "flag"), (GfDist, "ctx"), (GfPrecond, "dist"),
+               (GfPcgWork, "scal_h")]
+
+
+def check_abi(lib):
+    """Compare every ctypes mirror with the compiled header (size and offset of the last field)."""
+    for i, (T, last) in enumerate(ABI_STRUCTS):
+        size, off = c_i64(0), c_i64(0)
+        if lib.gf_abi_layout(i, C.byref(size), C.byref(off)) != 0:
+            raise GoldfishError("gf_abi_layout(%d) failed" % i)
+        if size.value != C.sizeof(T) or off.value != getattr(T, last).offset:
+            raise GoldfishError("ABI mismatch for %s: library %d/%d, binding %d/%d"
+                                % (T.__name__, size.value, off.value, C.sizeof(T), getattr(T, last).offset))
+
+
 # every symbol include/goldfish_b200.h declares, with its argument types
 SIGNATURES = {
     "gf_shell_assemble": [C.POINTER(GfModel), C.c_int, C.POINTER(GfShellOut), c_vp],
@@ -105,6 +122,7 @@ SIGNATURES = {
     "gf_penalty_gather_P": [C.POINTER(GfPenalty), C.POINTER(GfPenaltyP), c_vp],
     "gf_mask_vec": [C.POINTER(GfModel), c_vp, c_vp],
     "gf_spmv": [C.POINTER(GfCsr), c_vp, c_vp, c_f64, c_f64, c_vp],
+    "gf_spmv_node": [C.POINTER(GfCsr), c_vp, c_vp, c_i64, c_vp, c_vp, c_f64, c_f64, c_vp],
     "gf_spmv_t": [C.POINTER(GfCsr), C.POINTER(GfCsrT), c_vp, c_vp, c_f64, c_f64, c_vp],
     "gf_pcg": [C.POINTER(GfCsr), c_vp, c_vp, C.POINTER(GfPcgWork), C.POINTER(GfPrecond), C.POINTER(GfDist), c_f64, c_f64, C.c_int, C.c_int,
                C.POINTER(C.c_int), C.POINTER(c_f64), c_vp],
@@ -120,6 +138,7 @@ SIGNATURES = {
     "gf_reduce_wv": [c_i64, c_vp, c_vp, c_vp],
     "gf_last_error": [],
     "gf_version": [],
+    "gf_abi_layout": [C.c_int, C.POINTER(c_i64), C.POINTER(c_i64)],
     "gf_launch_count": [],
 }
 
@@ -145,6 +164,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_char_p if name == "gf_last_error" else (C.c_longlong if name == "gf_launch_count" else C.c_int)
+    check_abi(lib)                      # the ctypes mirrors above must match the compiled header
     _lib = lib
     return lib
 

@@ -404,6 +404,20 @@ class DeviceModel:
             capi.check(self.lib.gf_spmv(C.byref(cs), _ptr(x), _ptr(y), alpha, beta, st), "gf_spmv")
         return y
 
+    def spmv_node(self, x, y, alpha=1.0, beta=0.0):
+        """EXPERIMENTAL y = beta y + alpha K x with the node-wise kernel (gf_spmv_node: the three field rows of a
+        control point share one index / x read).  Not on the default path; scripts/gpu_spmv_node_check.py
+        compares it with gf_spmv."""
+        if getattr(self, "_node_rows", None) is None:
+            S = self.sym
+            row0 = np.concatenate([P.dof_off + np.arange(P.ncp, dtype=np.int64) for P in S.patches])
+            stride = np.concatenate([np.full(P.ncp, P.ncp, dtype=np.int32) for P in S.patches])
+            self._node_rows = (torch.from_numpy(row0).to(self.device), torch.from_numpy(stride).to(self.device))
+        r0, st = self._node_rows
+        capi.check(self.lib.gf_spmv_node(C.byref(self.K.c_struct()), _ptr(r0), _ptr(st), r0.numel(), _ptr(x), _ptr(y),
+                                         alpha, beta, self._stream()), "gf_spmv_node")
+        return y
+
     def spmv_global(self, A, x, y, alpha=1.0, beta=0.0, transpose=False):
         """y = beta y + alpha A x (or A^T x) with x, y replicated on every rank."""
         if self.dist is None:

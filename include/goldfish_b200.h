@@ -172,6 +172,11 @@ int gf_mask_vec(const GfModel* m, double* v, void* stream);
  *      operations/disp_imop.py:58-142) ---- */
 int gf_spmv(const GfCsr* A, const double* x, double* y, double alpha, double beta, void* stream);
 /* y = beta*y + alpha*A^T x through a host-built transpose map (deterministic gather) */
+/* EXPERIMENTAL (round-2 candidate for the default tangent product): node-wise product for
+ * matrices whose rows r0, r0+stride, r0+2*stride (the three displacement fields of one control point) share one
+ * column list; node_row0[n] = first row of node n, node_stride[n] = its patch's control-point count. */
+int gf_spmv_node(const GfCsr* A, const int64_t* node_row0, const int32_t* node_stride, int64_t n_nodes,
+                 const double* x, double* y, double alpha, double beta, void* stream);
 typedef struct GfCsrT { int64_t nrows, nnz; const int64_t* indptr; const int32_t* indices; const int64_t* perm; } GfCsrT;
 int gf_spmv_t(const GfCsr* A, const GfCsrT* At, const double* x, double* y, double alpha, double beta, void* stream);
 
@@ -270,6 +275,10 @@ int gf_reduce_wv(int64_t num_elements, const double* WV, double* out2_dev, void*
 
 const char* gf_last_error(void);
 int gf_version(void);
+/* sizeof / offsetof(last field) of the public structs, in declaration order (0 GfPatchDesc, 1 GfCsr, 2 GfModel,
+ * 3 GfShellOut, 4 GfPenalty, 5 GfPenaltyP, 6 GfCsrT, 7 GfSchwarz, 8 GfDist, 9 GfPrecond, 10 GfPcgWork): lets a
+ * binding verify its mirror of this header (tests/test_capi_symbols.py does, without a GPU). */
+int gf_abi_layout(int which, int64_t* size, int64_t* last_offset);
 /* number of kernels this library has launched so far (bench.py's gpu_launches) */
 long long gf_launch_count(void);
 

@@ -24,10 +24,18 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert built_lib.gf_version() >= 100
 
 
-def test_struct_layout_matches_header():
+def test_struct_layout_matches_header(built_lib):
+    """Every ctypes mirror against the compiled header: size and offset of the last field (gf_abi_layout is a
+    host-only export, so this runs without a GPU)."""
     from goldfish_b200 import _capi
     assert ctypes.sizeof(_capi.GfPatchDesc) == 18 * 4 + 5 * 8
     assert ctypes.sizeof(_capi.GfCsr) == 48
+    _capi.check_abi(built_lib)
+    for i, (T, last) in enumerate(_capi.ABI_STRUCTS):
+        size, off = ctypes.c_int64(0), ctypes.c_int64(0)
+        assert built_lib.gf_abi_layout(i, ctypes.byref(size), ctypes.byref(off)) == 0
+        assert (size.value, off.value) == (ctypes.sizeof(T), getattr(T, last).offset), T.__name__
+    assert built_lib.gf_abi_layout(99, ctypes.byref(size), ctypes.byref(off)) != 0
 
 
 def test_no_gpu_means_loud_failure():

@@ -80,3 +80,23 @@ def test_field_rows_of_a_control_point_share_one_column_list(case):
             own = c0[nl:nl + 3 * Sa].reshape(3, Sa)
             assert np.array_equal(own[1], own[0] + P.ncp) and np.array_equal(own[2], own[0] + 2 * P.ncp)
             assert own[0].min() >= P.dof_off and own[0].max() < P.dof_off + P.ncp
+
+
+def test_node_wise_product_addressing_emulated():
+    """numpy emulation of gf_spmv_node's addressing (node_row0 / node_stride as DeviceModel.spmv_node builds them):
+    index list of the field-0 row applied to the value streams of the three field rows == K x."""
+    pr, kw = cases.slr_small()
+    S = Symbolic(pr, **kw)
+    rng = np.random.default_rng(0)
+    vals = rng.standard_normal(S.K_indptr[-1]); x = rng.standard_normal(S.N)
+    K = sp.csr_matrix((vals, S.K_indices, S.K_indptr), shape=(S.N, S.N))
+    row0 = np.concatenate([P.dof_off + np.arange(P.ncp, dtype=np.int64) for P in S.patches])
+    stride = np.concatenate([np.full(P.ncp, P.ncp, dtype=np.int32) for P in S.patches])
+    y = np.zeros(S.N)
+    for r0, st in zip(row0, stride):
+        s0 = S.K_indptr[r0]; ln = S.K_indptr[r0 + 1] - s0
+        xv = x[S.K_indices[s0:s0 + ln]]
+        for i in range(3):
+            si = S.K_indptr[r0 + i * st]
+            y[r0 + i * st] = vals[si:si + ln] @ xv
+    assert len(row0) == S.n_scalar and np.abs(y - K @ x).max() < 1e-12
