@@ -40,21 +40,33 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-el", type=int, default=int(os.environ.get("GF_BENCH_NEL", "201")),
                     help="elements per patch side; 201 = BASELINE configs[2] (8 patches, ~1.03 M DOF)")
+    ap.add_argument("--topology", default="4x2", help="patches around x along the cylinder (4x2 = BASELINE configs[2]; 8x5 = 40 patches)")
     ap.add_argument("--cpu-n-el", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
-def workload_name(n_el):
-    return ("cylinder_4x2_ne%d: synthetic 8-patch non-matching bicubic NURBS cylinder (BASELINE configs[2]), 10 intersections, "
-            "shape fields 0,1,2 + per-patch thickness" % n_el)
+def topo(args):
+    a, b = args.topology.lower().split("x")
+    return int(a), int(b)
 
 
-def workload(n_el):
+def workload_name(n_el, n_circ=4, n_axial=2):
+    if (n_circ, n_axial) == (4, 2):
+        return ("cylinder_4x2_ne%d: synthetic 8-patch non-matching bicubic NURBS cylinder (BASELINE configs[2]), 12 intersections, "
+                "shape fields 0,1,2 + per-patch thickness" % n_el)
+    n_itf = n_circ * n_axial + n_circ * (n_axial - 1)
+    return ("cylinder_%dx%d_ne%d: synthetic %d-patch non-matching bicubic NURBS cylinder (BASELINE configs[3]-like, coupling-heavy), "
+            "%d intersections, shape fields 0,1,2 + per-patch thickness" % (n_circ, n_axial, n_el, n_circ * n_axial, n_itf))
+
+
+def workload(n_el, n_circ=4, n_axial=2):
+    """BASELINE configs[2] (default 4 x 2 patches); --topology 8x5 gives the 40-patch, 72-intersection stand-in for
+    configs[3] (n_el 286 there is ~10 M DOF)."""
     from goldfish_b200 import problems
-    pr = problems.cylinder(n_el=n_el, n_circ=4, n_axial=2, R=1.0, L=4.0, E=68e9, nu=0.35, h_th=1e-2,
+    pr = problems.cylinder(n_el=n_el, n_circ=n_circ, n_axial=n_axial, R=1.0, L=2.0 * n_axial, E=68e9, nu=0.35, h_th=1e-2,
                            pressure_like_load=(0.0, 0.0, -1.0e3), quad_deg_const=3, thickness_kind="const")
-    kw = dict(opt_field=[0, 1, 2], shopt_surf_inds=[list(range(8))] * 3)
+    kw = dict(opt_field=[0, 1, 2], shopt_surf_inds=[list(range(n_circ * n_axial))] * 3)
     return pr, kw
 
 
@@ -238,8 +250,8 @@ def cpu_reference_iteration(pr, kw):
 def run_reference(args, rank):
     if rank != 0:
         return
-    pr, kw = workload(args.cpu_n_el)
-    full_pr, _ = workload(args.n_el)
+    pr, kw = workload(args.cpu_n_el, *topo(args))
+    full_pr, _ = workload(args.n_el, *topo(args))
     from goldfish_b200 import problems
     N_full = problems.num_dofs(full_pr)
     times = []
@@ -255,7 +267,7 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": "analysis+adjoint iters/s", "value": val, "unit": "iters/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.n_el), "dofs": N_full},
+            "config": {"workload": workload_name(args.n_el, *topo(args)), "dofs": N_full},
             "cpu_baseline": {"value": val, "unit": "iters/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -280,7 +292,7 @@ def main():
     from goldfish_b200 import _capi as capi
     from goldfish_b200.device_model import DeviceModel
     lib = capi.load()
-    pr, kw = workload(args.n_el)
+    pr, kw = workload(args.n_el, *topo(args))
     dm = DeviceModel(pr, **kw)
     S = dm.sym
     cp, th = design_state(S)
@@ -371,7 +383,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(args.n_el),
+                "config": {"workload": workload_name(args.n_el, *topo(args)),
                            "dofs": int(S.N), "elements": int(S.num_elements), "nnz_K": int(dm.K.nnz), "quad_pts_per_element": int(nq),
                            "cache": "512 MB flush buffer written between timed kernel launches; step working set > L2 at n_el >= 64",
                            "parallelism": "1 GPU" if world == 1 else "patch-sharded over %d GPUs (rows + Schwarz blocks owned, vectors replicated, NCCL all-reduce)" % world},
@@ -394,7 +406,7 @@ def main():
         if world == 1:
             line["other_configs"] = small_configs(torch)
         if not args.no_cpu_baseline:
-            prs, kws = workload(args.cpu_n_el)
+            prs, kws = workload(args.cpu_n_el, *topo(args))
             dt, Ns = cpu_reference_iteration(prs, kws)
             v = (1.0 / dt) * (Ns / S.N)
             line["cpu_baseline"] = {"value": v, "unit": "iters/s", "cores": os.cpu_count(), "kind": "port",

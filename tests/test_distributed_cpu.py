@@ -149,3 +149,34 @@ def test_sharded_krylov_exchange_over_gloo():
         p.join(300)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+def test_forty_patch_topology_shards_over_eight_ranks():
+    """BASELINE configs[3] stand-in (bench.py --topology 8x5: 40 patches, 72 intersections): the symbolic phase,
+    the Schwarz blocks and the coarse level set up, and the 8-rank sharding covers every element, coupling
+    destination, row and block exactly once (several patches per rank, ragged loads)."""
+    import bench
+    from goldfish_b200.symbolic import Symbolic
+    from goldfish_b200.partition import lpt_partition, shard_symbolic
+    from goldfish_b200.schwarz import SchwarzSetup
+    from goldfish_b200 import coarse
+    pr, kw = bench.workload(5, 8, 5)
+    S = Symbolic(pr, **kw)
+    assert len(S.patches) == 40 and len(pr["interfaces"]) == 72
+    owner = lpt_partition([P.nel for P in S.patches], 8)
+    loads = np.bincount(owner, weights=[P.nel for P in S.patches], minlength=8)
+    assert loads.min() > 0 and loads.max() <= 1.25 * loads.mean()
+    elems, covered, nR, nK = [], np.zeros(S.N, dtype=int), 0, 0
+    for rank in range(8):
+        sh = shard_symbolic(S, owner, rank)
+        elems.append(np.asarray(sh["color_elem"]))
+        nR += sh["pen"]["nR"]; nK += sh["pen"]["nK"]
+        for b0, b1 in sh["own_ranges"]:
+            covered[b0:b1] += 1
+    assert np.array_equal(np.sort(np.concatenate(elems)), np.arange(S.num_elements))
+    assert np.all(covered == 1) and nR == S.pen["nR"] and nK == S.pen["nK"]
+    SW = SchwarzSetup(S)
+    per_rank = [sum(owner[b["patch"]] == r for b in SW.blocks) for r in range(8)]
+    assert sum(per_rank) == len(SW.blocks) == 40 and min(per_rank) >= 1
+    cpr, P = coarse.build(pr, nc=3)
+    assert P.shape == (S.N, Symbolic(cpr).N)
