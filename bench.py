@@ -405,7 +405,7 @@ def main():
                 "kernels": kernels, "clocks": cs.summary()}
         if world == 1:
             line["other_configs"] = small_configs(torch)
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # reported at N = 1 only (bench contract)
             prs, kws = workload(args.cpu_n_el, *topo(args))
             dt, Ns = cpu_reference_iteration(prs, kws)
             v = (1.0 / dt) * (Ns / S.N)
