@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--topology", default="4x2", help="patches around x along the cylinder (4x2 = BASELINE configs[2]; 8x5 = 40 patches)")
     ap.add_argument("--cpu-n-el", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the (untimed) parity checks at the benched size")
     return ap.parse_args()
 
 
@@ -136,6 +137,7 @@ class Step:
         self.gP = [torch.zeros(n, dtype=torch.float64, device=dm.device) for n in S.P_ncols]
         self.gT = torch.zeros(S.n_th, dtype=torch.float64, device=dm.device)
         self.info = {}
+        self.newton_rtol = 1e-3          # the reference's default (operations/disp_imop.py:38)
 
     def __call__(self, timers=None):
         import ctypes as C
@@ -147,16 +149,17 @@ class Step:
             if timers is not None:
                 e = torch.cuda.Event(enable_timing=True); e.record(); timers.append((name, e))
         mark("start")
-        dm.newton(max_it=30, rtol=1e-3)
+        dm.newton(max_it=30, rtol=self.newton_rtol)
         mark("newton (assemble R,K + factor + PCG per iteration)")
         kits = list(dm.newton_krylov_its)
+        trel = list(dm.newton_true_relres)
         dm.ensure(tangent=True, functionals=True, shape=True, thickness=True)   # K of the last Newton iterate is reused
         mark("linearize (K, W, V, dR/dCP x3, dR/dt, dW/d*)")
         self.rhs.copy_(dm.dWdu)
         capi.check(dm.lib.gf_mask_vec(C.byref(dm.model), C.c_void_p(self.rhs.data_ptr()), dm._stream()), "mask")
         dm.solve(self.rhs, self.lam)
         mark("adjoint solve")
-        kits.append(dm.last_krylov_its)
+        kits.append(dm.last_krylov_its); trel.append(dm.last_true_relres)
         for i in range(len(S.opt_field)):
             self.gP[i].copy_(dm.dWdP[i][:S.P_ncols[i]])
             dm.spmv_global(dm.P[i], self.lam, self.gP[i], alpha=-1.0, beta=1.0, transpose=True)
@@ -165,7 +168,8 @@ class Step:
         self.gT.copy_(dm.dWdt[:S.n_th])
         dm.spmv_global(dm.T, self.lam, self.gT, alpha=-1.0, beta=1.0, transpose=True)
         mark("gradient products (dR/dp)^T lam")
-        self.info = {"newton_its": len(dm.newton_history) - 1, "krylov_its": kits}
+        self.info = {"newton_its": len(dm.newton_history) - 1, "krylov_its": kits, "true_relres": trel,
+                     "gmres_fallback_used": bool(dm.fallback_used)}
 
 
 def e2e_step(nm, ops, cp_host, th_host):
@@ -200,6 +204,95 @@ def build_facade(pr, kw, symbolic=None):
     nm.set_residuals([ShellLoad(body_force=P["body_force"]) for P in pr["patches"]])
     nm._symbolic = symbolic          # same topology as the device-resident arm: reuse its symbolic phase
     return nm, (DispImOpeartion(nm), IntEnergyExOperation(nm), VolumeExOperation(nm))
+
+
+def parity_checks(dm, step, torch, world):
+    """Correctness evidence AT THE BENCHED SIZE (not timed): true residuals of the state and adjoint solves,
+    symmetry of the assembled tangent, and central finite differences of W_int (each side a full Newton solve)
+    against the adjoint total gradient -- the reference's own check (check_totals in
+    demos_csdl_alpha/thickness_opt/plate_const_th_opt_wint.py:220-223) -- for one patch thickness and one
+    shape direction.  Newton is converged to 1e-10 here so that FD and adjoint differentiate the same state."""
+    import ctypes as C
+    from goldfish_b200 import _capi as capi
+    S = dm.sym
+    out = {}
+    step.newton_rtol = 1e-10
+    step()
+    tr = step.info["true_relres"]
+    out["true_relres_state"] = max(tr[:-1]) if len(tr) > 1 else None
+    out["true_relres_adjoint"] = tr[-1]
+    out["recurrence_rtol"] = dm.krylov_rtol
+    W0 = float(dm.wv_sum[0].item())
+    gT = step.gT.clone(); gP = [g.clone() for g in step.gP]
+    # symmetry of K: |K x - K^T x| / |K x| for a random x (rows owned by this rank; summed over ranks inside spmv_global)
+    g = torch.Generator(device="cpu"); g.manual_seed(3)
+    x = torch.randn(S.N, dtype=torch.float64, generator=g).to(dm.device)
+    y1 = torch.zeros_like(x); y2 = torch.zeros_like(x)
+    dm.spmv_global(dm.K, x, y1); dm.spmv_global(dm.K, x, y2, transpose=True)
+    out["K_asymmetry"] = float(torch.linalg.vector_norm(y1 - y2) / torch.linalg.vector_norm(y1))
+
+    def W_at(theta=None, cp=None):
+        th0, cp0 = dm.theta.clone(), dm.cp.clone()
+        if theta is not None:
+            dm.theta.copy_(theta)
+        if cp is not None:
+            dm.cp.copy_(cp)
+        dm.touch()
+        dm.newton(max_it=30, rtol=1e-10)
+        W = float(dm.wv_sum[0].item())
+        dm.theta.copy_(th0); dm.cp.copy_(cp0); dm.touch()
+        return W
+    # (1) thickness of one patch (const thickness: one design variable per patch)
+    ip = min(3, S.n_th - 1)
+    h = 1e-3 * float(dm.theta[ip].item())
+    tp, tm = dm.theta.clone(), dm.theta.clone()
+    tp[ip] += h; tm[ip] -= h
+    fd_t = (W_at(theta=tp) - W_at(theta=tm)) / (2 * h)
+    out["fd_dWdt"] = {"dof": int(ip), "adjoint": float(gT[ip].item()), "central_fd": fd_t,
+                      "relerr": abs(fd_t - float(gT[ip].item())) / abs(float(gT[ip].item()))}
+    # (2) a smooth shape direction on patch 0, field 2 (z): bump sin(pi a/n_u) sin(pi b/n_v)
+    if S.opt_field:
+        f = S.opt_field[-1]; fi = S.opt_field.index(f)
+        P = S.patches[S.shopt_surf_inds[fi][0]]
+        I = np.tile(np.arange(P.n_u), P.n_v); J = np.repeat(np.arange(P.n_v), P.n_u)
+        d = np.sin(np.pi * I / (P.n_u - 1)) * np.sin(np.pi * J / (P.n_v - 1))
+        dvec = np.zeros(S.P_ncols[fi]); dvec[P.pcol_off[f]:P.pcol_off[f] + P.ncp] = d
+        dd = torch.from_numpy(dvec).to(dm.device)
+        adj = float((gP[fi] * dd).sum().item())
+        eps = 1e-4                         # metres; the cylinder has R = 1, t = 1e-2
+        dcp = torch.zeros_like(dm.cp).view(-1, 4)      # design variables = homogeneous coordinates cpFuncs[f] (update_CPIGA)
+        dcp[P.cp_off:P.cp_off + P.ncp, f] = torch.from_numpy(d).to(dm.device)
+        fd_p = (W_at(cp=(dm.cp.view(-1, 4) + eps * dcp).reshape(-1)) - W_at(cp=(dm.cp.view(-1, 4) - eps * dcp).reshape(-1))) / (2 * eps)
+        out["fd_dWdCP"] = {"field": int(f), "patch": int(P.index), "direction": "sin x sin bump", "adjoint": adj, "central_fd": fd_p,
+                           "relerr": abs(fd_p - adj) / abs(adj)}
+    out["fd_grad_relerr"] = max(v["relerr"] for k, v in out.items() if k.startswith("fd_d"))
+    out["W_int"] = W0
+    step.newton_rtol = 1e-3
+    return out
+
+
+def ranks_vs_single(torch, dist, world, rank, n_el=20):
+    """Sharded run against an unsharded run of the same (small) problem on every rank's own GPU:
+    max relative difference of u and of the total gradients (printed in the bench line at N > 1)."""
+    from goldfish_b200.device_model import DeviceModel
+    pr, kw = workload(n_el)
+    res = {}
+    outs = []
+    for distributed in (True, False):
+        dm = DeviceModel(pr, distributed=distributed, **kw)
+        cp, th = design_state(dm.sym)
+        dm.cp.copy_(torch.from_numpy(cp)); dm.set_theta(th)
+        st = Step(dm); st.newton_rtol = 1e-10
+        st()
+        outs.append((dm.u.clone(), [g.clone() for g in st.gP] + [st.gT.clone()], st.info["krylov_its"]))
+    (ua, ga, ka), (ub, gb, kb) = outs
+    rel = lambda a, b: float(torch.linalg.vector_norm(a - b) / torch.linalg.vector_norm(b))
+    res = {"n_el": n_el, "dofs": int(ua.numel()), "u": rel(ua, ub), "gradients": max(rel(a, b) for a, b in zip(ga, gb)),
+           "krylov_its_sharded": ka, "krylov_its_single": kb}
+    t = torch.tensor([res["u"], res["gradients"]], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res["u"], res["gradients"] = float(t[0]), float(t[1])
+    return res
 
 
 def small_configs(torch):
@@ -373,6 +466,11 @@ def main():
             phases[timers[i][0]] = phases.get(timers[i][0], 0.0) + timers[i - 1][1].elapsed_time(timers[i][1]) / len(step_timers)
     phases = {k: round(v, 2) for k, v in phases.items()}
     fac_ms = time_kernel(torch, lambda: dm.factor_preconditioner(), 2, flush)
+    parity = None
+    if not args.no_parity:
+        parity = parity_checks(dm, step, torch, world)
+        if world > 1:
+            parity["ranks_vs_single"] = ranks_vs_single(torch, dist, world, rank)
     kernels = {"phase_ms": phases, "precond_factor_ms": fac_ms, "spmv_ms": spmv_ms, "spmv_gbs": achieved, "sweeps_ms": sweep_ms, "sweeps_gbs": sweep_gbs,
                "assemble_RK_ms": asm_ms, "assemble_RK_material_tflops": asm_flops / (asm_ms * 1e-3) / 1e12,
                "assemble_RK_gbs_algorithmic": (8 * dm.K.nnz + 8 * (4 * S.n_scalar + S.N + S.n_th)) / (asm_ms * 1e-3) / 1e9,
@@ -402,6 +500,7 @@ def main():
                                   # ncu --set full of ONE k_spmv launch on this workload (profiles/r1_ncu_spmv_c3.txt)
                                   "traffic": 1887203640 if (args.n_el == 201 and world == 1) else None,
                                   "algorithmic_bytes": int(spmv_bytes)},
+                "parity": parity,
                 "kernels": kernels, "clocks": cs.summary()}
         if world == 1:
             line["other_configs"] = small_configs(torch)

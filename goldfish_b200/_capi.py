@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GF_LIB", os.path.join(_HERE, "libgoldfish_b200.so"))   # GF_LIB: tuning experiments only
 
 GF_OUT_R, GF_OUT_K, GF_OUT_W, GF_OUT_P, GF_OUT_T = 1, 2, 4, 8, 16
+GF_ERR_BADARG, GF_ERR_CUDA, GF_ERR_NOCONV, GF_ERR_BREAKDOWN, GF_ERR_NAN = 1, 2, 3, 4, 5
 GF_ERRORS = {1: "bad argument", 2: "CUDA error", 3: "not converged", 4: "breakdown", 5: "NaN"}
 
 c_i32, c_i64, c_f64, c_vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p
@@ -78,11 +79,8 @@ class GfSchwarz(C.Structure):
                 ("band", c_vp), ("band32", c_vp), ("invd", c_vp), ("y", c_vp), ("s", c_vp), ("barrier", c_vp), ("flag", c_vp)]
 
 
-ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_int, c_vp)
-
-
 class GfDist(C.Structure):
-    _fields_ = [("n_ranges", c_i32), ("pad_", c_i32), ("ranges_h", c_vp), ("allreduce", ALLREDUCE_FN), ("ctx", c_vp)]
+    _fields_ = [("n_ranges", c_i32), ("rank", c_i32), ("world", c_i32), ("pad_", c_i32), ("ranges_h", c_vp), ("comm", c_vp)]
 
 
 class GfPrecond(C.Structure):
@@ -95,10 +93,14 @@ class GfPcgWork(C.Structure):
                 ("scal", c_vp), ("partial", c_vp), ("scal_h", c_vp)]
 
 
+class GfGmresWork(C.Structure):
+    _fields_ = [("V", c_vp), ("z", c_vp), ("t", c_vp), ("hdev", c_vp), ("partial", c_vp), ("h_host", c_vp)]
+
+
 # (struct, last field) in the order of gf_abi_layout's ids
 ABI_STRUCTS = [(GfPatchDesc, "f"), (GfCsr, "vals"), (GfModel, "T"), (GfShellOut, "dt_el"), (GfPenalty, "K_pos"),
-               (GfPenaltyP, "field"), (GfCsrT, "perm"), (GfSchwarz, "flag"), (GfDist, "ctx"), (GfPrecond, "dist"),
-               (GfPcgWork, "scal_h")]
+               (GfPenaltyP, "field"), (GfCsrT, "perm"), (GfSchwarz, "flag"), (GfDist, "comm"), (GfPrecond, "dist"),
+               (GfPcgWork, "scal_h"), (GfGmresWork, "h_host")]
 
 
 def check_abi(lib):
@@ -126,6 +128,12 @@ SIGNATURES = {
     "gf_spmv_t": [C.POINTER(GfCsr), C.POINTER(GfCsrT), c_vp, c_vp, c_f64, c_f64, c_vp],
     "gf_pcg": [C.POINTER(GfCsr), c_vp, c_vp, C.POINTER(GfPcgWork), C.POINTER(GfPrecond), C.POINTER(GfDist), c_f64, c_f64, C.c_int, C.c_int,
                C.POINTER(C.c_int), C.POINTER(c_f64), c_vp],
+    "gf_gmres": [C.POINTER(GfCsr), c_vp, c_vp, C.POINTER(GfGmresWork), C.POINTER(GfPrecond), C.POINTER(GfDist), c_f64, C.c_int, C.c_int,
+                 C.POINTER(C.c_int), C.POINTER(c_f64), c_vp],
+    "gf_dist_unique_id": [c_vp],
+    "gf_dist_init": [C.POINTER(GfDist), c_vp, C.c_int, C.c_int],
+    "gf_dist_allreduce": [C.POINTER(GfDist), c_vp, c_i64, c_vp],
+    "gf_dist_destroy": [C.POINTER(GfDist)],
     "gf_schwarz_factor": [C.POINTER(GfSchwarz), C.POINTER(GfCsr), c_vp],
     "gf_schwarz_apply": [C.POINTER(GfSchwarz), c_vp, c_vp, c_i64, c_vp],
     "gf_schwarz_apply2": [C.POINTER(GfSchwarz), c_vp, c_vp, c_i64, C.POINTER(GfSchwarz), c_vp, c_vp, c_i64, c_vp],
@@ -136,6 +144,7 @@ SIGNATURES = {
     "gf_axpby": [c_i64, c_f64, c_vp, c_f64, c_vp, c_vp],
     "gf_dot": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp],
     "gf_reduce_wv": [c_i64, c_vp, c_vp, c_vp],
+    "gf_peak_fp64": [C.c_int, C.c_int, C.c_int, c_vp, C.POINTER(c_f64), c_vp],
     "gf_last_error": [],
     "gf_version": [],
     "gf_abi_layout": [C.c_int, C.POINTER(c_i64), C.POINTER(c_i64)],

@@ -390,12 +390,48 @@ __global__ void k_zero_list(const int32_t* list, int64_t n, double* v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[list[i]] = 0.0;
 }
 
+namespace gf {
+int dist_allreduce(const GfDist* d, double* buf, int64_t n, cudaStream_t st);   // gf_dist.cu
+
+// y = A x with x replicated: single process -> whole matrix (optionally fused dot partials dotv.y);
+// sharded -> owned row ranges, the rest of y zeroed, then summed over the ranks (NCCL all-reduce on `st`).
+static int apply_A(const GfCsr& A, const GfDist* dist, const double* x, double* y, const double* dotv,
+                   double* partial, int* npart, cudaStream_t st) {
+  const bool sharded = dist && dist->n_ranges > 0;
+  const int64_t n = A.nrows;
+  if (!sharded) {
+    const int gs = spmv_grid(n);
+    launch_spmv(gs, st, A, x, y, 1.0, 0.0, dotv, partial);
+    count_launch(1);
+    if (npart) *npart = gs;
+    return GF_OK;
+  }
+  cudaError_t e = cudaMemsetAsync(y, 0, (size_t)n * sizeof(double), st);
+  if (e != cudaSuccess) return set_cuda_error(e, "apply_A memset");
+  for (int q = 0; q < dist->n_ranges; ++q) {
+    const int64_t b0 = dist->ranges_h[2 * q], b1 = dist->ranges_h[2 * q + 1];
+    if (b1 <= b0) continue;
+    GfCsr sub = A; sub.indptr = A.indptr + b0; sub.nrows = b1 - b0;
+    launch_spmv(spmv_grid(sub.nrows), st, sub, x, y + b0, 1.0, 0.0, nullptr, nullptr);
+    count_launch(1);
+  }
+  int rc = dist_allreduce(dist, y, n, st);
+  if (rc) return rc;
+  if (dotv && partial) {
+    const int gv = vec_grid(n);
+    k_dot_partial<<<gv, RED_THREADS, 0, st>>>(n, dotv, y, partial);
+    count_launch(1);
+    if (npart) *npart = gv;
+  }
+  return GF_OK;
+}
+}  // namespace gf
+
 extern "C" int gf_precond_apply(const GfPrecond* pc, const double* r, double* z, int64_t n, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!pc->coarse) {
     int rc0 = gf_schwarz_apply(pc->fine, r, z, n, st);
-    if (rc0 == 0 && pc->dist && pc->dist->n_ranges > 0 && pc->dist->allreduce(1, pc->dist->ctx))
-      return set_error(GF_ERR_CUDA, "all-reduce of the preconditioned residual failed");
+    if (rc0 == 0 && pc->dist && pc->dist->n_ranges > 0) rc0 = dist_allreduce(pc->dist, z, n, st);
     return rc0;
   }
   int rc = gf_spmv(&pc->Rt, r, pc->rc, 1.0, 0.0, st);       // restriction r_c = P^T r
@@ -408,8 +444,8 @@ extern "C" int gf_precond_apply(const GfPrecond* pc, const double* r, double* z,
   rc = gf_schwarz_apply2(pc->fine, r, z, n, pc->coarse, pc->rc, pc->zc, pc->Rt.nrows, st);
   if (rc) return rc;
   if (pc->dist && pc->dist->n_ranges > 0) {                   // sum the ranks' block contributions
-    rc = pc->dist->allreduce(1, pc->dist->ctx);
-    if (rc) return set_error(GF_ERR_CUDA, "all-reduce of the preconditioned residual failed");
+    rc = dist_allreduce(pc->dist, z, n, st);
+    if (rc) return rc;
   }
   return gf_spmv(&pc->P, pc->zc, z, 1.0, 1.0, st);            // z += P z_c (coarse level is replicated)
 }
@@ -417,11 +453,10 @@ extern "C" int gf_precond_apply(const GfPrecond* pc, const double* r, double* z,
 extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, const GfPrecond* pre,
                       const GfDist* dist, double rtol, double atol, int max_it, int check_every, int* iters,
                       double* relres, void* stream) {
-  const bool sharded = dist && dist->n_ranges > 0;
   if (!A || !b || !x || !w) return set_error(GF_ERR_BADARG, "gf_pcg: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = A->nrows;
-  const int gv = vec_grid(n), gs = spmv_grid(n);
+  const int gv = vec_grid(n);
   double* part1 = w->partial;                 // pAp partials [MAX_PARTIAL]
   double* part2 = w->partial + MAX_PARTIAL;   // (rz, rr) partials [2*MAX_PARTIAL]
   if (check_every < 1) check_every = 1;
@@ -450,25 +485,9 @@ extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWor
   int rc = GF_ERR_NOCONV;
   while (it < max_it) {
     const int parity = it & 1;
-    int npart1 = gs;
-    if (!sharded) {
-      launch_spmv(gs, st, *A, w->p, w->Ap, 1.0, 0.0, w->p, part1);
-    } else {
-      // owned rows only, then sum over ranks; every rank then holds the full A p and
-      // computes the (identical) dot products itself -> no scalar all-reduce
-      e = cudaMemsetAsync(w->Ap, 0, (size_t)n * sizeof(double), st);
-      if (e != cudaSuccess) return set_cuda_error(e, "gf_pcg memset");
-      for (int q = 0; q < dist->n_ranges; ++q) {
-        const int64_t b0 = dist->ranges_h[2 * q], b1 = dist->ranges_h[2 * q + 1];
-        if (b1 <= b0) continue;
-        GfCsr sub = *A; sub.indptr = A->indptr + b0; sub.nrows = b1 - b0;
-        launch_spmv(spmv_grid(sub.nrows), st, sub, w->p, w->Ap + b0, 1.0, 0.0, nullptr, nullptr);
-        count_launch(1);
-      }
-      if (dist->allreduce(0, dist->ctx)) return set_error(GF_ERR_CUDA, "all-reduce of A p failed");
-      k_dot_partial<<<gv, RED_THREADS, 0, st>>>(n, w->p, w->Ap, part1);
-      npart1 = gv;
-    }
+    int npart1 = 0;
+    int rca = apply_A(*A, dist, w->p, w->Ap, w->p, part1, &npart1, st);
+    if (rca) return rca;
     k_pcg_update<<<gv, RED_THREADS, 0, st>>>(n, w->p, w->Ap, w->dinv, x, w->r, w->z, part1, npart1, w->scal,
                                              parity, part2);
     if (pre) {
@@ -478,7 +497,7 @@ extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWor
       count_launch(1);
     }
     k_pcg_dir<<<gv, RED_THREADS, 0, st>>>(n, w->z, w->p, part2, gv, w->scal, parity);
-    count_launch(3);
+    count_launch(2);
     ++it;
     if (it % check_every == 0 || it == max_it) {
       e = cudaMemcpyAsync(w->scal_h, w->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, st);
@@ -486,13 +505,191 @@ extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWor
       if (e != cudaSuccess) return set_cuda_error(e, "gf_pcg iteration");
       const double rr = w->scal_h[4], pAp = w->scal_h[6];
       if (!(rr == rr) || !(pAp == pAp)) { rc = set_error(GF_ERR_NAN, "gf_pcg: NaN in recurrence"); break; }
-      if (!(pAp > 0.0)) { rc = set_error(GF_ERR_BREAKDOWN, "gf_pcg: p.Ap <= 0 (matrix not SPD)"); break; }
       rel = sqrt(rr) / bnorm;
+      // convergence first: once r = 0 exactly (tiny systems, right-hand sides supported on identity rows)
+      // the later directions are p = 0 and p.Ap = 0 without any loss of definiteness
       if (rel < rtol || sqrt(rr) < atol) { rc = GF_OK; break; }
+      if (!(pAp > 0.0)) { rc = set_error(GF_ERR_BREAKDOWN, "gf_pcg: p.Ap <= 0 (matrix not SPD)"); break; }
     }
   }
   if (iters) *iters = it;
   if (relres) *relres = rel;
   if (rc == GF_ERR_NOCONV) set_error(rc, "gf_pcg: tolerance not reached within max_it");
+  return rc;
+}
+
+// ------------------------------------------------------------------ GMRES ----
+// Right-preconditioned restarted GMRES(m) with the same preconditioner: the fallback of the Krylov path when the
+// tangent is not positive definite (CG breaks down; the reference's LU, utils/opt_utils.py:176, still returns a
+// step).  Classical Gram-Schmidt applied twice (two fused multi-dot / multi-axpy passes per iteration, fixed
+// reduction trees); the (m+1) x m Hessenberg least-squares problem is updated on the host with Givens rotations.
+namespace gf {
+constexpr int GM_CHUNK = 8;
+// partial[blk][j] = sum over the CTA's entries of V_j . w, j in [0, k)
+__global__ void __launch_bounds__(RED_THREADS)
+k_mdot(int64_t n, const double* __restrict__ V, int64_t ld, int k, const double* __restrict__ w, double* partial) {
+  __shared__ double sh[32];
+  for (int j0 = 0; j0 < k; j0 += GM_CHUNK) {
+    double acc[GM_CHUNK];
+#pragma unroll
+    for (int q = 0; q < GM_CHUNK; ++q) acc[q] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const double wi = w[i];
+#pragma unroll
+      for (int q = 0; q < GM_CHUNK; ++q)
+        if (j0 + q < k) acc[q] = fma(V[(int64_t)(j0 + q) * ld + i], wi, acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < GM_CHUNK; ++q) {
+      if (j0 + q < k) {
+        const double sacc = block_sum(acc[q], sh);
+        if (threadIdx.x == 0) partial[(size_t)blockIdx.x * k + j0 + q] = sacc;
+      }
+    }
+  }
+}
+// h[j] (+)= sum_blk partial[blk][j]
+__global__ void __launch_bounds__(RED_THREADS)
+k_mdot_fin(const double* partial, int nblk, int k, double* h, int accumulate, double* hlast) {
+  __shared__ double sh[32];
+  for (int j = 0; j < k; ++j) {
+    const double sacc = sum_partials(partial + j, nblk, k, sh);
+    if (threadIdx.x == 0) { h[j] = accumulate ? h[j] + sacc : sacc; hlast[j] = sacc; }
+  }
+}
+// w -= sum_j c[j] V_j
+__global__ void __launch_bounds__(RED_THREADS)
+k_maxpy(int64_t n, const double* __restrict__ V, int64_t ld, int k, const double* __restrict__ c, double sign,
+        double* __restrict__ w, int overwrite) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double acc = overwrite ? 0.0 : w[i];
+    for (int j = 0; j < k; ++j) acc = fma(sign * c[j], V[(int64_t)j * ld + i], acc);
+    w[i] = acc;
+  }
+}
+// out = in * (1 / sqrt(*nrm2))
+__global__ void __launch_bounds__(RED_THREADS)
+k_scale_inv_norm(int64_t n, const double* __restrict__ in, const double* nrm2, double* __restrict__ out) {
+  const double s = (*nrm2 > 0.0) ? 1.0 / sqrt(*nrm2) : 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = in[i] * s;
+}
+}  // namespace gf
+
+extern "C" int gf_gmres(const GfCsr* A, const double* b, double* x, const GfGmresWork* w, const GfPrecond* pre,
+                        const GfDist* dist, double rtol, int restart, int max_it, int* iters, double* relres,
+                        void* stream) {
+  if (!A || !b || !x || !w || restart < 1 || restart > 128) return set_error(GF_ERR_BADARG, "gf_gmres: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = A->nrows;
+  const int gv = vec_grid(n), m = restart;
+  double* V = w->V;            // [(m+1)][n]
+  double* hd = w->hdev;        // [m+2] h column | [m+2] last pass | [1] norm^2
+  double* hh = w->h_host;      // pinned mirror
+  // host Hessenberg (column major, (m+1) x m), Givens cs/sn, rhs g
+  double* H = (double*)malloc(sizeof(double) * (size_t)(m + 1) * m);
+  double* cs = (double*)malloc(sizeof(double) * m), *sn = (double*)malloc(sizeof(double) * m);
+  double* g = (double*)malloc(sizeof(double) * (m + 1)), *yv = (double*)malloc(sizeof(double) * (m + 1));
+  int rc = GF_ERR_NOCONV, it = 0;
+  double rel = 1.0, bnorm = 0.0;
+  cudaError_t e = cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), st);
+  bool first = true;
+  auto fetch = [&](int cnt) -> int {
+    cudaError_t e2 = cudaMemcpyAsync(hh, hd, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st);
+    if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
+    return e2 == cudaSuccess ? GF_OK : set_cuda_error(e2, "gf_gmres fetch");
+  };
+  while (it < max_it && e == cudaSuccess) {
+    // r = b - A x  (x = 0 in the first cycle)
+    if (first) {
+      e = cudaMemcpyAsync(w->t, b, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    } else {
+      int r1 = apply_A(*A, dist, x, w->t, nullptr, nullptr, nullptr, st);
+      if (r1) { rc = r1; break; }
+      k_axpby<<<gv, RED_THREADS, 0, st>>>(n, 1.0, b, -1.0, w->t);
+      count_launch(1);
+    }
+    k_dot_partial<<<gv, RED_THREADS, 0, st>>>(n, w->t, w->t, w->partial);
+    k_finalize<<<1, RED_THREADS, 0, st>>>(w->partial, gv, 1, hd + 2 * (m + 2));
+    k_scale_inv_norm<<<gv, RED_THREADS, 0, st>>>(n, w->t, hd + 2 * (m + 2), V);
+    count_launch(3);
+    if ((rc = fetch(2 * (m + 2) + 1)) != GF_OK) break;
+    const double beta = sqrt(hh[2 * (m + 2)]);
+    if (first) {
+      bnorm = beta; first = false;
+      if (!(bnorm > 0.0)) { rc = (bnorm == 0.0) ? GF_OK : set_error(GF_ERR_NAN, "gf_gmres: right-hand side is not finite"); rel = 0.0; break; }
+    }
+    rel = beta / bnorm;
+    rc = GF_ERR_NOCONV;
+    if (rel < rtol) { rc = GF_OK; break; }
+    for (int i = 0; i <= m; ++i) g[i] = 0.0;
+    g[0] = beta;
+    int j = 0;
+    for (; j < m && it < max_it; ++j) {
+      double* vj = V + (int64_t)j * n; double* wv = V + (int64_t)(j + 1) * n;
+      const double* zsrc = vj;
+      if (pre) {
+        int r1 = gf_precond_apply(pre, vj, w->z, n, st);
+        if (r1) { rc = r1; goto done; }
+        zsrc = w->z;
+      }
+      { int r1 = apply_A(*A, dist, zsrc, wv, nullptr, nullptr, nullptr, st); if (r1) { rc = r1; goto done; } }
+      // CGS2: h = V^T w, w -= V h, twice (second pass accumulates into h)
+      for (int pass = 0; pass < 2; ++pass) {
+        k_mdot<<<gv, RED_THREADS, 0, st>>>(n, V, n, j + 1, wv, w->partial);
+        k_mdot_fin<<<1, RED_THREADS, 0, st>>>(w->partial, gv, j + 1, hd, pass, hd + (m + 2));
+        k_maxpy<<<gv, RED_THREADS, 0, st>>>(n, V, n, j + 1, hd + (m + 2), -1.0, wv, 0);
+        count_launch(3);
+      }
+      k_dot_partial<<<gv, RED_THREADS, 0, st>>>(n, wv, wv, w->partial);
+      k_finalize<<<1, RED_THREADS, 0, st>>>(w->partial, gv, 1, hd + 2 * (m + 2));
+      k_scale_inv_norm<<<gv, RED_THREADS, 0, st>>>(n, wv, hd + 2 * (m + 2), wv);
+      count_launch(3);
+      if ((rc = fetch(2 * (m + 2) + 1)) != GF_OK) goto done;
+      rc = GF_ERR_NOCONV;
+      double* Hj = H + (size_t)j * (m + 1);
+      for (int i = 0; i <= j; ++i) Hj[i] = hh[i];
+      Hj[j + 1] = sqrt(hh[2 * (m + 2)]);
+      if (!(Hj[j + 1] == Hj[j + 1])) { rc = set_error(GF_ERR_NAN, "gf_gmres: NaN in Arnoldi"); goto done; }
+      for (int i = 0; i < j; ++i) {        // previous rotations
+        const double t0 = cs[i] * Hj[i] + sn[i] * Hj[i + 1];
+        Hj[i + 1] = -sn[i] * Hj[i] + cs[i] * Hj[i + 1]; Hj[i] = t0;
+      }
+      const double den = hypot(Hj[j], Hj[j + 1]);
+      cs[j] = den > 0 ? Hj[j] / den : 1.0; sn[j] = den > 0 ? Hj[j + 1] / den : 0.0;
+      Hj[j] = den; Hj[j + 1] = 0.0;
+      g[j + 1] = -sn[j] * g[j]; g[j] = cs[j] * g[j];
+      ++it;
+      rel = fabs(g[j + 1]) / bnorm;
+      if (rel < rtol) { ++j; break; }
+    }
+    // y = H^-1 g (upper triangular), x += M^-1 (V y)
+    for (int i = j - 1; i >= 0; --i) {
+      double sacc = g[i];
+      for (int q = i + 1; q < j; ++q) sacc -= H[(size_t)q * (m + 1) + i] * yv[q];
+      yv[i] = sacc / H[(size_t)i * (m + 1) + i];
+    }
+    for (int i = 0; i < j; ++i) hh[i] = yv[i];
+    e = cudaMemcpyAsync(hd, hh, sizeof(double) * j, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) break;
+    k_maxpy<<<gv, RED_THREADS, 0, st>>>(n, V, n, j, hd, 1.0, w->t, 1);
+    count_launch(1);
+    if (pre) {
+      int r1 = gf_precond_apply(pre, w->t, w->z, n, st);
+      if (r1) { rc = r1; break; }
+      k_axpby<<<gv, RED_THREADS, 0, st>>>(n, 1.0, w->z, 1.0, x);
+    } else {
+      k_axpby<<<gv, RED_THREADS, 0, st>>>(n, 1.0, w->t, 1.0, x);
+    }
+    count_launch(1);
+    e = cudaStreamSynchronize(st);         // hh is reused by the next cycle
+    if (rel < rtol) { rc = GF_OK; break; }
+  }
+done:
+  free(H); free(cs); free(sn); free(g); free(yv);
+  if (e != cudaSuccess) return set_cuda_error(e, "gf_gmres");
+  if (iters) *iters = it;
+  if (relres) *relres = rel;
+  if (rc == GF_ERR_NOCONV) set_error(rc, "gf_gmres: tolerance not reached within max_it");
   return rc;
 }

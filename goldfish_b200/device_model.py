@@ -25,6 +25,27 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else C.c_void_p(0)
 
 
+_NCCL_COMM = {}
+
+
+def _nccl_comm(lib, dist, device):
+    """The library-side NCCL communicator of this process (one per device), see csrc/gf_dist.cu."""
+    key = str(device)
+    if key not in _NCCL_COMM:
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if dist.get_rank() == 0:
+            buf = (C.c_ubyte * 128)()
+            capi.check(lib.gf_dist_unique_id(buf), "gf_dist_unique_id")
+            idt = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+        idt = idt.to(device)
+        dist.broadcast(idt, src=0)
+        raw = bytes(idt.cpu().numpy().tobytes())
+        d = capi.GfDist()
+        capi.check(lib.gf_dist_init(C.byref(d), C.c_char_p(raw), dist.get_rank(), dist.get_world_size()), "gf_dist_init")
+        _NCCL_COMM[key] = d.comm
+    return _NCCL_COMM[key]
+
+
 class DeviceCsr:
     """CSR matrix whose arrays live in HBM."""
 
@@ -197,6 +218,12 @@ class DeviceModel:
         # 1e-9..1e-10, and every parity test also passes at 1e-10, so 1e-11 keeps a margin without idle iterations
         self.krylov_rtol = float(_os.environ.get("GF_KRYLOV_RTOL", "1e-11"))
         self.krylov_max_it = 200000
+        # target for the TRUE relative residual |b - K x| / |b| of every solve (None: trust the recurrence)
+        self.true_rtol = float(_os.environ.get("GF_TRUE_RTOL", "1e-10"))
+        self.max_refine = 2
+        self.gmres_fallback = True
+        self.fallback_used = False
+        self.last_true_relres = None
         self.krylov_check_every = 50 if precond == "jacobi" else 5
         self.last_krylov_its = 0
         self.last_relres = 0.0
@@ -235,11 +262,16 @@ class DeviceModel:
             self.pen_HuX = torch.zeros(ne * 324, dtype=torch.float64, device=self.device)
             q.g, q.Huu, q.HuX = _ptr(self.pen_g), _ptr(self.pen_Huu), _ptr(self.pen_HuX)
             q.nR, q.nK = pen["nR"], pen["nK"]
-            for pp in self._shard["penP"]:
-                if pp.get("n_dest", 0) == 0:
-                    self.penP.append(None)
+            for pp, pp_all in zip(self._shard["penP"], S.penP):
+                if pp_all.get("n_dest", 0) == 0:
+                    self.penP.append(None)           # no penalty part at all (the same on every rank)
                     continue
                 M = DeviceCsr(S.N, S.P_ncols[S.opt_field.index(pp["field"])], pp["indptr"], pp["indices"], self.device)
+                if pp.get("n_dest", 0) == 0:
+                    # this rank owns none of the destinations: keep an all-zero part so that every rank
+                    # holds the same number of parts (one all-reduce per part in DeviceMat products)
+                    self.penP.append((M, None))
+                    continue
                 s = capi.GfPenaltyP()
                 s.n_dest = pp["n_dest"]
                 arrs = [up(pp[k] if len(pp[k]) else np.zeros(1, pp[k].dtype)) for k in ("ptr", "item_eval", "item_code", "pos")]
@@ -361,7 +393,8 @@ class DeviceModel:
                 for pp in self.penP:
                     if pp is not None:
                         pp[0].vals.zero_()
-                        capi.check(lib.gf_penalty_gather_P(C.byref(self.pen_struct), C.byref(pp[1]), st), "gather_P")
+                        if pp[1] is not None:
+                            capi.check(lib.gf_penalty_gather_P(C.byref(self.pen_struct), C.byref(pp[1]), st), "gather_P")
         if residual:
             self.allreduce(self.R)
             capi.check(lib.gf_mask_vec(C.byref(self.model), _ptr(self.R), st), "gf_mask_vec")
@@ -512,37 +545,67 @@ class DeviceModel:
         self._schwarz().debug_flags = {"auto": 0, "single": 4, "group": 8, "single_nocluster": 4 | 16}[mode]
 
     def _dist_struct(self):
+        """GfDist: owned row ranges + the library's own NCCL communicator (created once per process from a unique
+        id broadcast over torch.distributed; shared by every model of the process)."""
         if getattr(self, "_dist_c", None) is None:
             d = capi.GfDist()
             if self.dist is not None:
                 self._ranges_h = np.ascontiguousarray(self.own_ranges if len(self.own_ranges) else np.zeros((1, 2), np.int64))
                 d.n_ranges = max(1, len(self.own_ranges))
                 d.ranges_h = self._ranges_h.ctypes.data_as(C.c_void_p)
-
-                def _ar(which, ctx):
-                    try:
-                        self.dist.all_reduce(self.w_Ap if which == 0 else self.w_z)
-                        return 0
-                    except Exception as e:  # surfaced as a GF error by the caller
-                        print("all-reduce failed:", e)
-                        return 1
-                self._ar_cb = capi.ALLREDUCE_FN(_ar)
-                d.allreduce = self._ar_cb
+                d.comm, d.rank, d.world = _nccl_comm(self.lib, self.dist, self.device), self.rank, self.world
             self._dist_c = d
         return self._dist_c
+
+    def _gmres(self, b, x, rtol, max_it, restart=60):
+        """Right-preconditioned GMRES(restart) with the current preconditioner (fallback of _krylov)."""
+        n = self.sym.N
+        if getattr(self, "_gm", None) is None:
+            dv = self.device
+            t = dict(V=torch.empty((restart + 1) * n, dtype=torch.float64, device=dv),
+                     z=torch.empty(n, dtype=torch.float64, device=dv), t=torch.empty(n, dtype=torch.float64, device=dv),
+                     hdev=torch.zeros(2 * (restart + 2) + 1, dtype=torch.float64, device=dv),
+                     partial=torch.zeros(1024 * (restart + 1), dtype=torch.float64, device=dv),
+                     h_host=torch.zeros(2 * (restart + 2) + 1, dtype=torch.float64).pin_memory())
+            w = capi.GfGmresWork()
+            w.V, w.z, w.t, w.hdev, w.partial = [_ptr(t[k]) for k in ("V", "z", "t", "hdev", "partial")]
+            w.h_host = C.c_void_p(t["h_host"].data_ptr())
+            self._gm = (w, t, restart)
+        w, _, restart = self._gm
+        pre = C.byref(self._precond_struct()) if self.precond == "schwarz" else None
+        its = C.c_int(0); rel = C.c_double(0.0)
+        rc = self.lib.gf_gmres(C.byref(self.K.c_struct()), _ptr(b), _ptr(x), C.byref(w), pre, C.byref(self._dist_struct()),
+                               rtol, restart, max_it, C.byref(its), C.byref(rel), self._stream())
+        capi.check(rc, "gf_gmres")
+        return its.value, rel.value
 
     def refresh_coarse(self):
         """Re-assemble and re-factor the coarse level at the next preconditioner set-up."""
         self._coarse_factored = False
 
-    def factor_preconditioner(self):
+    def factor_preconditioner(self, _reference=False):
         """(Re)build the preconditioner from the current K values."""
         st = self._stream()
         self.replicate_K()
         cs = self.K.c_struct()
         if self.precond == "schwarz":
             pc = self._precond_struct()
-            capi.check(self.lib.gf_schwarz_factor(C.byref(self._schwarz()), C.byref(cs), st), "gf_schwarz_factor")
+            rc = self.lib.gf_schwarz_factor(C.byref(self._schwarz()), C.byref(cs), st)
+            if rc == capi.GF_ERR_BREAKDOWN and not _reference:
+                # The tangent at this state is not positive definite (e.g. past a buckling point), so its
+                # blocks have no Cholesky factor.  Precondition with the tangent of the SAME design at u = 0
+                # instead (SPD) and let the Krylov fallback (GMRES) deal with the indefinite operator.
+                u_keep = self.u.clone()
+                self.u.zero_()
+                self.assemble(tangent=True)
+                self.factor_preconditioner(_reference=True)
+                self.u.copy_(u_keep)
+                self.assemble(tangent=True)
+                self.precond_is_reference = True
+                self._fact_version = self._K_version
+                return
+            capi.check(rc, "gf_schwarz_factor")
+            self.precond_is_reference = bool(_reference)
             if self._coarse is not None and not self._coarse_factored:
                 # The coarse operator is the reference configuration's tangent (u = 0, initial design) on the
                 # coarse spline space: it does not depend on the state, so it is assembled and factored once
@@ -562,8 +625,12 @@ class DeviceModel:
             z = torch.empty_like(r)
         if not self._sw_factored:
             self.factor_preconditioner()
-        capi.check(self.lib.gf_precond_apply(C.byref(self._precond_struct()), _ptr(r), _ptr(z), self.sym.N, self._stream()),
+        # sharded runs sum the ranks' contributions in the PCG work vector z: run there and copy out
+        zz = self.w_z if self.dist is not None else z
+        capi.check(self.lib.gf_precond_apply(C.byref(self._precond_struct()), _ptr(r), _ptr(zz), self.sym.N, self._stream()),
                    "gf_precond_apply")
+        if zz is not z:
+            z.copy_(zz)
         return z
 
     def solve(self, b, x=None, rtol=None, max_it=None, refactor=None):
@@ -572,19 +639,49 @@ class DeviceModel:
         otherwise the last factorisation is reused (lagged preconditioner)."""
         if x is None:
             x = torch.empty_like(b)
-        st = self._stream()
-        cs = self.K.c_struct()
         if refactor or not self._sw_factored or (self.eager_refactor and self._fact_version != self._K_version):
             self.factor_preconditioner()
+        rtol = self.krylov_rtol if rtol is None else rtol
+        its, rel = self._krylov(b, x, rtol, max_it)
+        self.last_krylov_its, self.last_relres = its, rel
+        # The recurrence residual of CG drifts from b - K x on these systems (kappa ~ 1e10..1e12): measure the
+        # TRUE residual with one more product and, while it is above the target, solve for a correction on it
+        # (iterative refinement; the reference's LU solve is exact to ~kappa*eps, utils/opt_utils.py:176).
+        self.last_true_relres = None
+        if self.true_rtol is not None:
+            if getattr(self, "_w_res", None) is None:
+                self._w_res, self._w_cor = torch.empty_like(b), torch.empty_like(b)
+            bn = self.dot(b, b) ** 0.5
+            for k in range(self.max_refine + 1):
+                self._w_res.copy_(b)
+                self.spmv_global(self.K, x, self._w_res, alpha=-1.0, beta=1.0)
+                tr = (self.dot(self._w_res, self._w_res) ** 0.5 / bn) if bn > 0 else 0.0
+                self.last_true_relres = tr
+                if tr <= self.true_rtol or k == self.max_refine:
+                    break
+                its2, _ = self._krylov(self._w_res, self._w_cor, max(min(1e-2, 0.1 * self.true_rtol / tr), rtol), max_it)
+                self.last_krylov_its += its2
+                self.axpby(1.0, self._w_cor, 1.0, x)
+        return x
+
+    def _krylov(self, b, x, rtol, max_it=None):
+        """One Krylov solve of K x = b from x = 0: PCG; on breakdown (p.Ap <= 0: the tangent is indefinite, e.g. past
+        a buckling point, where the reference's LU still returns a step) the same system is handed to
+        right-preconditioned restarted GMRES with the same preconditioner."""
+        st = self._stream()
+        cs = self.K.c_struct()
         pre = C.byref(self._precond_struct()) if self.precond == "schwarz" else None
         its = C.c_int(0); rel = C.c_double(0.0)
+        max_it = self.krylov_max_it if max_it is None else max_it
         rc = self.lib.gf_pcg(C.byref(cs), _ptr(b), _ptr(x), C.byref(self.pcg_work), pre, C.byref(self._dist_struct()),
-                             self.krylov_rtol if rtol is None else rtol, 0.0,
-                             self.krylov_max_it if max_it is None else max_it, self.krylov_check_every,
-                             C.byref(its), C.byref(rel), st)
-        self.last_krylov_its, self.last_relres = its.value, rel.value
+                             rtol, 0.0, max_it, self.krylov_check_every, C.byref(its), C.byref(rel), st)
+        if rc == capi.GF_ERR_BREAKDOWN and self.gmres_fallback:
+            n_it = its.value
+            its2, rel2 = self._gmres(b, x, rtol, max_it)
+            self.fallback_used = True
+            return n_it + its2, rel2
         capi.check(rc, "gf_pcg")
-        return x
+        return its.value, rel.value
 
     def dRdCP_matrix(self, i):
         """dR/dCP of opt-field slot i as one handle (shell + penalty parts)."""
@@ -597,7 +694,7 @@ class DeviceModel:
         self.u.zero_()
         self.touch()
         ref = None
-        hist, kits = [], []
+        hist, kits, trel = [], [], []
         du = torch.empty_like(self.u)
         rhs = torch.empty_like(self.u)
         for it in range(max_it + 1):
@@ -617,8 +714,8 @@ class DeviceModel:
                 raise capi.GoldfishNotConverged("Nonlinear solver failed to converge in %d iterations" % max_it)
             self.axpby(-1.0, self.R, 0.0, rhs)
             self.solve(rhs, du, refactor=(it == 0))
-            kits.append(self.last_krylov_its)
+            kits.append(self.last_krylov_its); trel.append(self.last_true_relres)
             self.axpby(1.0, du, 1.0, self.u)
             self.touch()
-        self.newton_history, self.newton_krylov_its = hist, kits
+        self.newton_history, self.newton_krylov_its, self.newton_true_relres = hist, kits, trel
         return self.u

@@ -230,18 +230,21 @@ int gf_dot_slot0(int64_t n, const double* x, const double* y, double* partial2, 
  * `fine` = overlapping patch blocks, `coarse` = ONE block holding the factor of
  * the coarse-spline operator (same shells + coupling re-discretised on a coarser
  * knot vector by the same kernels), P = knot-insertion prolongation, Rt = P^T. */
-/* Patch-sharded multi-GPU runs (one process per GPU): vectors are replicated, matrix
- * rows / Schwarz blocks are owned.  The library computes the owned part of A p and of
- * the preconditioned residual and asks the host (torch.distributed over NCCL) to
- * sum them across ranks:  which = 0 -> work->Ap, which = 1 -> work->z. */
-typedef int (*gf_allreduce_fn)(int which, void* ctx);
+/* Patch-sharded multi-GPU runs (one process per GPU, SURVEY.md section 8e): vectors are replicated, matrix
+ * rows / Schwarz blocks are owned.  The library computes the owned part of A p and of the
+ * preconditioned residual and sums them over the ranks itself: NCCL all-reduce over NVLink, issued on the
+ * compute stream from inside the Krylov loop (no host callback).  The host only carries the 128-byte unique
+ * id from rank 0 to the others over its own process group (torch.distributed broadcast). */
 typedef struct GfDist {
   int32_t n_ranges;               /* 0 = single process                               */
-  int32_t pad_;
+  int32_t rank, world, pad_;
   const int64_t* ranges_h;        /* HOST [n_ranges][2] owned row ranges [begin, end)  */
-  gf_allreduce_fn allreduce;
-  void* ctx;
+  void* comm;                     /* ncclComm_t, set by gf_dist_init                   */
 } GfDist;
+int gf_dist_unique_id(void* id128);                                     /* rank 0: ncclGetUniqueId            */
+int gf_dist_init(GfDist* d, const void* id128, int rank, int world);    /* collective: ncclCommInitRank       */
+int gf_dist_allreduce(const GfDist* d, double* buf, int64_t n, void* stream);   /* in-place FP64 sum          */
+int gf_dist_destroy(GfDist* d);
 
 typedef struct GfPrecond {
   const GfSchwarz* fine;
@@ -268,15 +271,32 @@ int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, const
            double* relres, void* stream);
 int gf_jacobi_setup(const GfCsr* A, double* dinv, void* stream);
 
+/* Right-preconditioned restarted GMRES(restart) on K x = b with the same preconditioner: the fallback when
+ * the tangent is indefinite and CG reports GF_ERR_BREAKDOWN (the reference's LU still returns a Newton step
+ * there, utils/opt_utils.py:176).  `iters` counts matrix-vector products. */
+typedef struct GfGmresWork {
+  double* V;          /* [(restart+1)][n] Krylov basis                              */
+  double* z; double* t;  /* [n] each                                               */
+  double* hdev;       /* [2*(restart+2)+1] device scalars                           */
+  double* partial;    /* [1024*(restart+1)] per-CTA partial sums                    */
+  double* h_host;     /* pinned host [2*(restart+2)+1]                              */
+} GfGmresWork;
+int gf_gmres(const GfCsr* A, const double* b, double* x, const GfGmresWork* w, const GfPrecond* precond,
+             const GfDist* dist, double rtol, int restart, int max_it, int* iters, double* relres, void* stream);
+
 /* small vector helpers on device */
 int gf_axpby(int64_t n, double a, const double* x, double b, double* y, void* stream);
 int gf_dot(int64_t n, const double* x, const double* y, double* partial, double* out_dev, void* stream);
 int gf_reduce_wv(int64_t num_elements, const double* WV, double* out2_dev, void* stream);
 
+/* FP64 peak micro-benchmarks (mode 0: DFMA chains, 1: DMMA m8n8k4): one launch of `grid` x 256 threads; the
+ * caller times it with CUDA events; *flops receives the operation count.  Measurement infrastructure. */
+int gf_peak_fp64(int mode, int grid, int iters, double* out, double* flops, void* stream);
+
 const char* gf_last_error(void);
 int gf_version(void);
 /* sizeof / offsetof(last field) of the public structs, in declaration order (0 GfPatchDesc, 1 GfCsr, 2 GfModel,
- * 3 GfShellOut, 4 GfPenalty, 5 GfPenaltyP, 6 GfCsrT, 7 GfSchwarz, 8 GfDist, 9 GfPrecond, 10 GfPcgWork): lets a
+ * 3 GfShellOut, 4 GfPenalty, 5 GfPenaltyP, 6 GfCsrT, 7 GfSchwarz, 8 GfDist, 9 GfPrecond, 10 GfPcgWork, 11 GfGmresWork): lets a
  * binding verify its mirror of this header (tests/test_capi_symbols.py does, without a GPU). */
 int gf_abi_layout(int which, int64_t* size, int64_t* last_offset);
 /* number of kernels this library has launched so far (bench.py's gpu_launches) */

@@ -644,12 +644,30 @@ class OracleModel:
         return np.concatenate(out)
 
     # ---------------------------------------------------------------- solves
-    def solve(self, K, b, transpose=False):
-        """solve_Ax_b / solve_ATx_b: sparse LU."""
-        A = K.T.tocsc() if transpose else K.tocsc()
-        return spla.splu(A).solve(np.asarray(b, dtype=np.float64))
+    def solve(self, K, b, transpose=False, refine=0):
+        """solve_Ax_b / solve_ATx_b: sparse LU (utils/opt_utils.py:176,204).
 
-    def solve_nonlinear(self, max_it=30, rtol=1e-3, verbose=False):
+        refine > 0: that many steps of iterative refinement with the residual
+        accumulated in extended precision (numpy longdouble).  The reference's MUMPS
+        solve has none; the goldens use it so that they hold the solution of the
+        linear system itself (kappa ~ 1e12 on the C1 plate makes a bare LU solve
+        good to ~2e-8 only), which is what an iterative solver converges to."""
+        A = (K.T if transpose else K).tocsr()
+        lu = spla.splu(A.tocsc())
+        b = np.asarray(b, dtype=np.float64)
+        x = lu.solve(b)
+        if refine:
+            rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))
+            data = A.data.astype(np.longdouble)
+            for _ in range(refine):
+                prod = data * x.astype(np.longdouble)[A.indices]
+                r = b.astype(np.longdouble)
+                Ax = np.zeros(A.shape[0], dtype=np.longdouble)
+                np.add.at(Ax, rows, prod)
+                x = x + lu.solve(np.asarray(r - Ax, dtype=np.float64))
+        return x
+
+    def solve_nonlinear(self, max_it=30, rtol=1e-3, verbose=False, refine=0):
         """PENGoLINS solve_nonlinear_nonmatching_problem(iga_dofs=True,
         zero_mortar_funcs=True): Newton from u = 0."""
         self.u = np.zeros(self.N)
@@ -669,7 +687,7 @@ class OracleModel:
             if it == max_it:
                 break
             K = self.stiffness()
-            du = self.solve(K, -R)
+            du = self.solve(K, -R, refine=refine)
             self.u = self.u + du
         self.newton_history = hist
         return self.u.copy()

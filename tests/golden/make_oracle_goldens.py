@@ -5,6 +5,9 @@ SURVEY.md section 4) and cannot run here, so these are outputs of the CPU
 restatement -- "parity unpinned" -- used (a) to keep the oracle from drifting
 and (b) to check the CUDA path at the full C1/C2 sizes without re-running the
 slow oracle on the GPU box.     python tests/golden/make_oracle_goldens.py
+The LU solves (Newton steps and adjoint) are iteratively refined with an extended-precision
+residual (OracleModel.solve(refine=3)): the goldens hold the solution of the linear systems
+themselves, so the CUDA path is held to north_star's 1e-8 on C1 as well (kappa ~ 1.5e12).
 """
 import os, sys
 import numpy as np
@@ -28,10 +31,10 @@ def make(name, pr, kw):
         A = m.dRdCP(f, kw["shopt_surf_inds"][i])
         out["P%d_indptr" % f] = A.indptr; out["P%d_indices" % f] = A.indices; out["P%d_data" % f] = A.data
         out["dWdP%d" % f] = m.dWdCP(f, kw["shopt_surf_inds"][i]); out["dVdP%d" % f] = m.dVdCP(f, kw["shopt_surf_inds"][i])
-    un = m.solve_nonlinear(max_it=30, rtol=1e-3)
+    un = m.solve_nonlinear(max_it=30, rtol=1e-3, refine=3)
     out.update(u_newton=un, newton_hist=np.array(m.newton_history))
     # adjoint total derivative of W_int w.r.t. thickness dofs at the Newton state
-    Kn = m.stiffness(); lam = m.solve(Kn, m.dWdu(apply_bcs=True), transpose=True)
+    Kn = m.stiffness(); lam = m.solve(Kn, m.dWdu(apply_bcs=True), transpose=True, refine=3)
     out.update(W_newton=m.energy(), lam=lam, dWdt_total=m.dWdt() - m.dRdt().T @ lam)
     np.savez_compressed(os.path.join(HERE, name + "_golden.npz"), **out)
     print(name, m.N, "K nnz", K.nnz, "newton its", len(m.newton_history) - 1, "W", out["W_newton"])

@@ -91,11 +91,12 @@ def test_baseline_configs_match_goldens(DM, case, gold):
     lam = dm.solve(rhs)
     tot = dm.dWdt[:dm.sym.n_th].clone()
     dm.spmv(dm.T, lam, tot, alpha=-1.0, beta=1.0, transpose=True)
-    # C1's tangent has kappa_1 ~ 1.5e12: the reference-style LU adjoint itself moves by 2e-8 under
-    # one step of iterative refinement (DESIGN.md "Parity tolerances"), so the golden is only
-    # defined to that level; C2 (kappa ~ 1e9) is held to north_star's 1e-8.
-    tol = 2e-7 if case == "plate_c1" else TOL_SOL
-    assert np.linalg.norm(tot.cpu().numpy() - g["dWdt_total"]) < tol * np.linalg.norm(g["dWdt_total"])
+    # C1's tangent has kappa_1 ~ 1.5e12; the golden's LU solves are iteratively refined with an extended-precision
+    # residual (tests/golden/make_oracle_goldens.py) and DeviceModel.solve refines on the TRUE residual, so both
+    # configurations are held to north_star's 1e-8.
+    assert dm.last_true_relres is not None and dm.last_true_relres < 1e-9
+    assert np.linalg.norm(lam.cpu().numpy() - g["lam"]) < TOL_SOL * np.linalg.norm(g["lam"])
+    assert np.linalg.norm(tot.cpu().numpy() - g["dWdt_total"]) < TOL_SOL * np.linalg.norm(g["dWdt_total"])
 
 
 def test_schwarz_and_jacobi_pcg_agree(DM):
