@@ -88,19 +88,23 @@ class GfPrecond(C.Structure):
                 ("rc", c_vp), ("zc", c_vp), ("bc_c", c_vp), ("n_bc_c", c_i64), ("dist", C.POINTER(GfDist))]
 
 
+class GfNodeRows(C.Structure):
+    _fields_ = [("row0", c_vp), ("stride", c_vp), ("n", c_i64)]
+
+
 class GfPcgWork(C.Structure):
     _fields_ = [("r", c_vp), ("z", c_vp), ("p", c_vp), ("Ap", c_vp), ("dinv", c_vp),
-                ("scal", c_vp), ("partial", c_vp), ("scal_h", c_vp)]
+                ("scal", c_vp), ("partial", c_vp), ("scal_h", c_vp), ("nodes", GfNodeRows)]
 
 
 class GfGmresWork(C.Structure):
-    _fields_ = [("V", c_vp), ("z", c_vp), ("t", c_vp), ("hdev", c_vp), ("partial", c_vp), ("h_host", c_vp)]
+    _fields_ = [("V", c_vp), ("z", c_vp), ("t", c_vp), ("hdev", c_vp), ("partial", c_vp), ("h_host", c_vp), ("nodes", GfNodeRows)]
 
 
 # (struct, last field) in the order of gf_abi_layout's ids
 ABI_STRUCTS = [(GfPatchDesc, "f"), (GfCsr, "vals"), (GfModel, "T"), (GfShellOut, "dt_el"), (GfPenalty, "K_pos"),
                (GfPenaltyP, "field"), (GfCsrT, "perm"), (GfSchwarz, "flag"), (GfDist, "comm"), (GfPrecond, "dist"),
-               (GfPcgWork, "scal_h"), (GfGmresWork, "h_host")]
+               (GfPcgWork, "nodes"), (GfGmresWork, "nodes")]
 
 
 def check_abi(lib):

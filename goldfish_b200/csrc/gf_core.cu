@@ -43,8 +43,8 @@ extern "C" int gf_abi_layout(int which, int64_t* size, int64_t* last_offset) {
     case 7: GF_LAYOUT(GfSchwarz, flag);
     case 8: GF_LAYOUT(GfDist, comm);
     case 9: GF_LAYOUT(GfPrecond, dist);
-    case 10: GF_LAYOUT(GfPcgWork, scal_h);
-    case 11: GF_LAYOUT(GfGmresWork, h_host);
+    case 10: GF_LAYOUT(GfPcgWork, nodes);
+    case 11: GF_LAYOUT(GfGmresWork, nodes);
     default: return gf::set_error(GF_ERR_BADARG, "gf_abi_layout: unknown struct id");
   }
 #undef GF_LAYOUT

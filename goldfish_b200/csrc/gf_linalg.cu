@@ -290,9 +290,12 @@ __global__ void k_bc_diag(GfModel M, double diag) {
 // of 12.  Lane partition and reduction per row are those of k_spmv_simple, so y is bitwise the same.
 __global__ void __launch_bounds__(256)
 k_spmv_node(GfCsr A, const int64_t* __restrict__ node_row0, const int32_t* __restrict__ node_stride, int64_t n_nodes,
-            const double* __restrict__ x, double* __restrict__ y, double alpha, double beta) {
+            const double* __restrict__ x, double* __restrict__ y, double alpha, double beta,
+            const double* __restrict__ dotv, double* __restrict__ partial) {
+  __shared__ double sh[32];
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  double dacc = 0.0;
   for (int64_t nd = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; nd < n_nodes; nd += nwarps) {
     const int64_t r0 = node_row0[nd], st = node_stride[nd];
     const int64_t s0 = A.indptr[r0], len = A.indptr[r0 + 1] - s0;
@@ -310,7 +313,12 @@ k_spmv_node(GfCsr A, const int64_t* __restrict__ node_row0, const int32_t* __res
       double v = alpha * (lane == 0 ? a0 : (lane == 1 ? a1 : a2));
       if (beta != 0.0) v = fma(beta, y[r], v);
       y[r] = v;
+      if (dotv) dacc = fma(dotv[r], v, dacc);
     }
+  }
+  if (partial) {
+    const double b = block_sum(dacc, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = b;
   }
 }
 
@@ -329,7 +337,8 @@ extern "C" int gf_spmv_node(const GfCsr* A, const int64_t* node_row0, const int3
                             const double* x, double* y, double alpha, double beta, void* stream) {
   if (!A || !node_row0 || !node_stride || !x || !y) return set_error(GF_ERR_BADARG, "gf_spmv_node: null argument");
   if (n_nodes == 0) return GF_OK;
-  k_spmv_node<<<spmv_grid(n_nodes), 256, 0, (cudaStream_t)stream>>>(*A, node_row0, node_stride, n_nodes, x, y, alpha, beta);
+  k_spmv_node<<<spmv_grid(n_nodes), 256, 0, (cudaStream_t)stream>>>(*A, node_row0, node_stride, n_nodes, x, y, alpha, beta,
+                                                                    nullptr, nullptr);
   return check_launch("k_spmv_node");
 }
 
@@ -395,11 +404,20 @@ int dist_allreduce(const GfDist* d, double* buf, int64_t n, cudaStream_t st);   
 
 // y = A x with x replicated: single process -> whole matrix (optionally fused dot partials dotv.y);
 // sharded -> owned row ranges, the rest of y zeroed, then summed over the ranks (NCCL all-reduce on `st`).
-static int apply_A(const GfCsr& A, const GfDist* dist, const double* x, double* y, const double* dotv,
-                   double* partial, int* npart, cudaStream_t st) {
+static int apply_A(const GfCsr& A, const GfDist* dist, const GfNodeRows* nodes, const double* x, double* y,
+                   const double* dotv, double* partial, int* npart, cudaStream_t st) {
   const bool sharded = dist && dist->n_ranges > 0;
+  const bool nodewise = nodes && nodes->n > 0 && nodes->row0 && nodes->stride;
   const int64_t n = A.nrows;
   if (!sharded) {
+    if (nodewise) {
+      // the three field rows of a control point share one column list: one index / x read per three non-zeros
+      const int gs = spmv_grid(nodes->n);
+      k_spmv_node<<<gs, 256, 0, st>>>(A, nodes->row0, nodes->stride, nodes->n, x, y, 1.0, 0.0, dotv, partial);
+      count_launch(1);
+      if (npart) *npart = gs;
+      return GF_OK;
+    }
     const int gs = spmv_grid(n);
     launch_spmv(gs, st, A, x, y, 1.0, 0.0, dotv, partial);
     count_launch(1);
@@ -408,12 +426,17 @@ static int apply_A(const GfCsr& A, const GfDist* dist, const double* x, double* 
   }
   cudaError_t e = cudaMemsetAsync(y, 0, (size_t)n * sizeof(double), st);
   if (e != cudaSuccess) return set_cuda_error(e, "apply_A memset");
-  for (int q = 0; q < dist->n_ranges; ++q) {
-    const int64_t b0 = dist->ranges_h[2 * q], b1 = dist->ranges_h[2 * q + 1];
-    if (b1 <= b0) continue;
-    GfCsr sub = A; sub.indptr = A.indptr + b0; sub.nrows = b1 - b0;
-    launch_spmv(spmv_grid(sub.nrows), st, sub, x, y + b0, 1.0, 0.0, nullptr, nullptr);
+  if (nodewise) {                              // `nodes` lists the control points of the owned patches
+    k_spmv_node<<<spmv_grid(nodes->n), 256, 0, st>>>(A, nodes->row0, nodes->stride, nodes->n, x, y, 1.0, 0.0, nullptr, nullptr);
     count_launch(1);
+  } else {
+    for (int q = 0; q < dist->n_ranges; ++q) {
+      const int64_t b0 = dist->ranges_h[2 * q], b1 = dist->ranges_h[2 * q + 1];
+      if (b1 <= b0) continue;
+      GfCsr sub = A; sub.indptr = A.indptr + b0; sub.nrows = b1 - b0;
+      launch_spmv(spmv_grid(sub.nrows), st, sub, x, y + b0, 1.0, 0.0, nullptr, nullptr);
+      count_launch(1);
+    }
   }
   int rc = dist_allreduce(dist, y, n, st);
   if (rc) return rc;
@@ -486,7 +509,7 @@ extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWor
   while (it < max_it) {
     const int parity = it & 1;
     int npart1 = 0;
-    int rca = apply_A(*A, dist, w->p, w->Ap, w->p, part1, &npart1, st);
+    int rca = apply_A(*A, dist, &w->nodes, w->p, w->Ap, w->p, part1, &npart1, st);
     if (rca) return rca;
     k_pcg_update<<<gv, RED_THREADS, 0, st>>>(n, w->p, w->Ap, w->dinv, x, w->r, w->z, part1, npart1, w->scal,
                                              parity, part2);
@@ -604,7 +627,7 @@ extern "C" int gf_gmres(const GfCsr* A, const double* b, double* x, const GfGmre
     if (first) {
       e = cudaMemcpyAsync(w->t, b, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st);
     } else {
-      int r1 = apply_A(*A, dist, x, w->t, nullptr, nullptr, nullptr, st);
+      int r1 = apply_A(*A, dist, &w->nodes, x, w->t, nullptr, nullptr, nullptr, st);
       if (r1) { rc = r1; break; }
       k_axpby<<<gv, RED_THREADS, 0, st>>>(n, 1.0, b, -1.0, w->t);
       count_launch(1);
@@ -633,7 +656,7 @@ extern "C" int gf_gmres(const GfCsr* A, const double* b, double* x, const GfGmre
         if (r1) { rc = r1; goto done; }
         zsrc = w->z;
       }
-      { int r1 = apply_A(*A, dist, zsrc, wv, nullptr, nullptr, nullptr, st); if (r1) { rc = r1; goto done; } }
+      { int r1 = apply_A(*A, dist, &w->nodes, zsrc, wv, nullptr, nullptr, nullptr, st); if (r1) { rc = r1; goto done; } }
       // CGS2: h = V^T w, w -= V h, twice (second pass accumulates into h)
       for (int pass = 0; pass < 2; ++pass) {
         k_mdot<<<gv, RED_THREADS, 0, st>>>(n, V, n, j + 1, wv, w->partial);

@@ -183,6 +183,14 @@ class DeviceModel:
         w = capi.GfPcgWork()
         w.r, w.z, w.p, w.Ap, w.dinv = [_ptr(t) for t in (self.w_r, self.w_z, self.w_p, self.w_Ap, self.w_dinv)]
         w.scal, w.partial, w.scal_h = _ptr(self.w_scal), _ptr(self.w_partial), C.c_void_p(self.w_scal_h.data_ptr())
+        # node-wise tangent product: control points of the owned patches (all of them on one GPU)
+        own_p = [P for P in S.patches if self.owner[P.index] == self.rank]
+        row0 = np.concatenate([P.dof_off + np.arange(P.ncp, dtype=np.int64) for P in own_p]) if own_p else np.zeros(0, np.int64)
+        stride = np.concatenate([np.full(P.ncp, P.ncp, dtype=np.int32) for P in own_p]) if own_p else np.zeros(0, np.int32)
+        self._node_rows = (up(row0), up(stride))
+        import os as _osn
+        if _osn.environ.get("GF_SPMV_ROWWISE", "0") != "1":
+            w.nodes.row0, w.nodes.stride, w.nodes.n = _ptr(self._node_rows[0]), _ptr(self._node_rows[1]), len(row0)
         self.pcg_work = w
         if precond not in ("schwarz", "jacobi"):
             raise ValueError("Undefined preconditioner: {}".format(precond))
@@ -438,14 +446,9 @@ class DeviceModel:
         return y
 
     def spmv_node(self, x, y, alpha=1.0, beta=0.0):
-        """EXPERIMENTAL y = beta y + alpha K x with the node-wise kernel (gf_spmv_node: the three field rows of a
-        control point share one index / x read).  Not on the default path; scripts/gpu_spmv_node_check.py
-        compares it with gf_spmv."""
-        if getattr(self, "_node_rows", None) is None:
-            S = self.sym
-            row0 = np.concatenate([P.dof_off + np.arange(P.ncp, dtype=np.int64) for P in S.patches])
-            stride = np.concatenate([np.full(P.ncp, P.ncp, dtype=np.int32) for P in S.patches])
-            self._node_rows = (torch.from_numpy(row0).to(self.device), torch.from_numpy(stride).to(self.device))
+        """y = beta y + alpha K x with the node-wise kernel the Krylov solvers use (gf_spmv_node: the three field
+        rows of a control point share one index / x read; bitwise the same y as gf_spmv,
+        scripts/gpu_spmv_node_check.py).  Rows of the owned patches only in sharded runs."""
         r0, st = self._node_rows
         capi.check(self.lib.gf_spmv_node(C.byref(self.K.c_struct()), _ptr(r0), _ptr(st), r0.numel(), _ptr(x), _ptr(y),
                                          alpha, beta, self._stream()), "gf_spmv_node")
@@ -570,6 +573,7 @@ class DeviceModel:
             w = capi.GfGmresWork()
             w.V, w.z, w.t, w.hdev, w.partial = [_ptr(t[k]) for k in ("V", "z", "t", "hdev", "partial")]
             w.h_host = C.c_void_p(t["h_host"].data_ptr())
+            w.nodes = self.pcg_work.nodes
             self._gm = (w, t, restart)
         w, _, restart = self._gm
         pre = C.byref(self._precond_struct()) if self.precond == "schwarz" else None

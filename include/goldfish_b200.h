@@ -257,12 +257,19 @@ typedef struct GfPrecond {
 } GfPrecond;
 int gf_precond_apply(const GfPrecond* pc, const double* r, double* z, int64_t n, void* stream);
 
+/* Node-wise row structure of the tangent: rows row0[n], row0[n]+stride[n], row0[n]+2 stride[n] (the three
+ * displacement fields of control point n) share one column list, so the Krylov product reads each column index
+ * and each x entry once per three non-zeros (9.33 B per non-zero instead of 12; bitwise the same y as gf_spmv).
+ * Sharded runs list the control points of the owned patches only.  n = 0: plain row-wise product. */
+typedef struct GfNodeRows { const int64_t* row0; const int32_t* stride; int64_t n; } GfNodeRows;
+
 typedef struct GfPcgWork {
   double* r; double* z; double* p; double* Ap;  /* [n] each */
   double* dinv;       /* [n] inverse diagonal (Jacobi) or 3x3 blocks, see precond */
   double* scal;       /* [16] device scalars                                        */
   double* partial;    /* [4096*4] per-CTA partial sums                              */
   double* scal_h;     /* pinned host [16]                                           */
+  GfNodeRows nodes;
 } GfPcgWork;
 /* Preconditioned CG on K x = b (K symmetric: nonmatching_opt.py:804-809).
  * Replaces solve_nonmatching_mat(..., 'direct') (utils/opt_utils.py:176,204). */
@@ -280,6 +287,7 @@ typedef struct GfGmresWork {
   double* hdev;       /* [2*(restart+2)+1] device scalars                           */
   double* partial;    /* [1024*(restart+1)] per-CTA partial sums                    */
   double* h_host;     /* pinned host [2*(restart+2)+1]                              */
+  GfNodeRows nodes;
 } GfGmresWork;
 int gf_gmres(const GfCsr* A, const double* b, double* x, const GfGmresWork* w, const GfPrecond* precond,
              const GfDist* dist, double rtol, int restart, int max_it, int* iters, double* relres, void* stream);

@@ -53,4 +53,9 @@ def test_gmres_matches_pcg_on_spd_system(built_lib):
     x_gm = torch.empty_like(b)
     its, rel = dm._gmres(b, x_gm, 1e-12, 2000)
     assert rel < 1e-12 and its > 0
-    assert float(torch.linalg.vector_norm(x_gm - x_cg) / torch.linalg.vector_norm(x_cg)) < 1e-8
+    # GMRES minimises the residual: with kappa(K) ~ 1e10 a 1e-12 residual bounds the error far less tightly than
+    # CG's energy-norm minimisation does, so compare residuals, and solutions only loosely
+    r = b.clone()
+    dm.spmv(dm.K, x_gm, r, alpha=-1.0, beta=1.0)
+    assert float(torch.linalg.vector_norm(r) / torch.linalg.vector_norm(b)) < 1e-11
+    assert float(torch.linalg.vector_norm(x_gm - x_cg) / torch.linalg.vector_norm(x_cg)) < 1e-2
