@@ -98,7 +98,7 @@ class GfPcgWork(C.Structure):
 
 
 class GfGmresWork(C.Structure):
-    _fields_ = [("V", c_vp), ("z", c_vp), ("t", c_vp), ("hdev", c_vp), ("partial", c_vp), ("h_host", c_vp), ("nodes", GfNodeRows)]
+    _fields_ = [("V", c_vp), ("Z", c_vp), ("t", c_vp), ("hdev", c_vp), ("partial", c_vp), ("h_host", c_vp), ("nodes", GfNodeRows)]
 
 
 # (struct, last field) in the order of gf_abi_layout's ids

@@ -542,7 +542,7 @@ extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWor
 }
 
 // ------------------------------------------------------------------ GMRES ----
-// Right-preconditioned restarted GMRES(m) with the same preconditioner: the fallback of the Krylov path when the
+// Flexible (right-preconditioned) restarted GMRES(m) with the same preconditioner: the fallback of the Krylov path when the
 // tangent is not positive definite (CG breaks down; the reference's LU, utils/opt_utils.py:176, still returns a
 // step).  Classical Gram-Schmidt applied twice (two fused multi-dot / multi-axpy passes per iteration, fixed
 // reduction trees); the (m+1) x m Hessenberg least-squares problem is updated on the host with Givens rotations.
@@ -652,9 +652,13 @@ extern "C" int gf_gmres(const GfCsr* A, const double* b, double* x, const GfGmre
       double* vj = V + (int64_t)j * n; double* wv = V + (int64_t)(j + 1) * n;
       const double* zsrc = vj;
       if (pre) {
-        int r1 = gf_precond_apply(pre, vj, w->z, n, st);
+        // FLEXIBLE variant: z_j = M^-1 v_j is kept.  The preconditioner multiplies FP32 panels, so it is linear
+        // only to ~1e-7; re-applying it to the combination V y (plain right preconditioning) would add an error
+        // of that relative size times |V y|, far above the residual on these kappa ~ 1e10 systems.
+        double* zj = w->Z + (int64_t)j * n;
+        int r1 = gf_precond_apply(pre, vj, zj, n, st);
         if (r1) { rc = r1; goto done; }
-        zsrc = w->z;
+        zsrc = zj;
       }
       { int r1 = apply_A(*A, dist, &w->nodes, zsrc, wv, nullptr, nullptr, nullptr, st); if (r1) { rc = r1; goto done; } }
       // CGS2: h = V^T w, w -= V h, twice (second pass accumulates into h)
@@ -695,15 +699,7 @@ extern "C" int gf_gmres(const GfCsr* A, const double* b, double* x, const GfGmre
     for (int i = 0; i < j; ++i) hh[i] = yv[i];
     e = cudaMemcpyAsync(hd, hh, sizeof(double) * j, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) break;
-    k_maxpy<<<gv, RED_THREADS, 0, st>>>(n, V, n, j, hd, 1.0, w->t, 1);
-    count_launch(1);
-    if (pre) {
-      int r1 = gf_precond_apply(pre, w->t, w->z, n, st);
-      if (r1) { rc = r1; break; }
-      k_axpby<<<gv, RED_THREADS, 0, st>>>(n, 1.0, w->z, 1.0, x);
-    } else {
-      k_axpby<<<gv, RED_THREADS, 0, st>>>(n, 1.0, w->t, 1.0, x);
-    }
+    k_maxpy<<<gv, RED_THREADS, 0, st>>>(n, pre ? w->Z : V, n, j, hd, 1.0, x, 0);     // x += Z y  (V y without preconditioner)
     count_launch(1);
     e = cudaStreamSynchronize(st);         // hh is reused by the next cycle
     if (rel < rtol) { rc = GF_OK; break; }

@@ -227,8 +227,9 @@ class DeviceModel:
         self.krylov_rtol = float(_os.environ.get("GF_KRYLOV_RTOL", "1e-11"))
         self.krylov_max_it = 200000
         # target for the TRUE relative residual |b - K x| / |b| of every solve (None: trust the recurrence)
-        self.true_rtol = float(_os.environ.get("GF_TRUE_RTOL", "1e-10"))
-        self.max_refine = 2
+        self.true_rtol = float(_os.environ.get("GF_TRUE_RTOL", "1e-8"))
+        self.pass_rtol = float(_os.environ.get("GF_PASS_RTOL", "1e-6"))       # recurrence tolerance of the first pass
+        self.max_refine = 3
         self.gmres_fallback = True
         self.fallback_used = False
         self.last_true_relres = None
@@ -560,18 +561,18 @@ class DeviceModel:
             self._dist_c = d
         return self._dist_c
 
-    def _gmres(self, b, x, rtol, max_it, restart=60):
+    def _gmres(self, b, x, rtol, max_it, restart=30):
         """Right-preconditioned GMRES(restart) with the current preconditioner (fallback of _krylov)."""
         n = self.sym.N
-        if getattr(self, "_gm", None) is None:
+        if getattr(self, "_gm", None) is None or self._gm[2] != restart:
             dv = self.device
             t = dict(V=torch.empty((restart + 1) * n, dtype=torch.float64, device=dv),
-                     z=torch.empty(n, dtype=torch.float64, device=dv), t=torch.empty(n, dtype=torch.float64, device=dv),
+                     Z=torch.empty(restart * n, dtype=torch.float64, device=dv), t=torch.empty(n, dtype=torch.float64, device=dv),
                      hdev=torch.zeros(2 * (restart + 2) + 1, dtype=torch.float64, device=dv),
                      partial=torch.zeros(1024 * (restart + 1), dtype=torch.float64, device=dv),
                      h_host=torch.zeros(2 * (restart + 2) + 1, dtype=torch.float64).pin_memory())
             w = capi.GfGmresWork()
-            w.V, w.z, w.t, w.hdev, w.partial = [_ptr(t[k]) for k in ("V", "z", "t", "hdev", "partial")]
+            w.V, w.Z, w.t, w.hdev, w.partial = [_ptr(t[k]) for k in ("V", "Z", "t", "hdev", "partial")]
             w.h_host = C.c_void_p(t["h_host"].data_ptr())
             w.nodes = self.pcg_work.nodes
             self._gm = (w, t, restart)
@@ -645,27 +646,33 @@ class DeviceModel:
             x = torch.empty_like(b)
         if refactor or not self._sw_factored or (self.eager_refactor and self._fact_version != self._K_version):
             self.factor_preconditioner()
-        rtol = self.krylov_rtol if rtol is None else rtol
-        its, rel = self._krylov(b, x, rtol, max_it)
-        self.last_krylov_its, self.last_relres = its, rel
-        # The recurrence residual of CG drifts from b - K x on these systems (kappa ~ 1e10..1e12): measure the
-        # TRUE residual with one more product and, while it is above the target, solve for a correction on it
-        # (iterative refinement; the reference's LU solve is exact to ~kappa*eps, utils/opt_utils.py:176).
+        # CG's recurrence residual drifts from b - K x on these systems (kappa ~ 1e10..1e12: after ~80 iterations the
+        # TRUE residual sits orders of magnitude above a 1e-11 recurrence residual), so the solve is a short
+        # sequence of passes with residual replacement: each pass runs PCG from x = 0 on the true residual of the
+        # previous iterate, to a tolerance relative to THAT residual, and the true residual is measured with one
+        # extra product after every pass.  Same total iteration count as one long pass; a true residual below
+        # `true_rtol` (the reference's LU solve, utils/opt_utils.py:176, is exact to ~kappa*eps).
         self.last_true_relres = None
-        if self.true_rtol is not None:
-            if getattr(self, "_w_res", None) is None:
-                self._w_res, self._w_cor = torch.empty_like(b), torch.empty_like(b)
-            bn = self.dot(b, b) ** 0.5
-            for k in range(self.max_refine + 1):
-                self._w_res.copy_(b)
-                self.spmv_global(self.K, x, self._w_res, alpha=-1.0, beta=1.0)
-                tr = (self.dot(self._w_res, self._w_res) ** 0.5 / bn) if bn > 0 else 0.0
-                self.last_true_relres = tr
-                if tr <= self.true_rtol or k == self.max_refine:
-                    break
-                its2, _ = self._krylov(self._w_res, self._w_cor, max(min(1e-2, 0.1 * self.true_rtol / tr), rtol), max_it)
-                self.last_krylov_its += its2
-                self.axpby(1.0, self._w_cor, 1.0, x)
+        if rtol is not None or self.true_rtol is None:
+            its, rel = self._krylov(b, x, self.krylov_rtol if rtol is None else rtol, max_it)
+            self.last_krylov_its, self.last_relres = its, rel
+            return x
+        if getattr(self, "_w_res", None) is None:
+            self._w_res, self._w_cor = torch.empty_like(b), torch.empty_like(b)
+        bn = self.dot(b, b) ** 0.5
+        its, rel = self._krylov(b, x, self.pass_rtol, max_it)
+        self.last_krylov_its, self.last_relres = its, rel
+        for k in range(self.max_refine + 1):
+            self._w_res.copy_(b)
+            self.spmv_global(self.K, x, self._w_res, alpha=-1.0, beta=1.0)
+            tr = (self.dot(self._w_res, self._w_res) ** 0.5 / bn) if bn > 0 else 0.0
+            self.last_true_relres = tr
+            if tr <= self.true_rtol or k == self.max_refine:
+                break
+            its2, rel2 = self._krylov(self._w_res, self._w_cor, min(1e-1, max(0.3 * self.true_rtol / tr, 1e-9)), max_it)
+            self.last_krylov_its += its2
+            self.last_relres = rel2 * tr
+            self.axpby(1.0, self._w_cor, 1.0, x)
         return x
 
     def _krylov(self, b, x, rtol, max_it=None):

@@ -278,12 +278,13 @@ int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, const
            double* relres, void* stream);
 int gf_jacobi_setup(const GfCsr* A, double* dinv, void* stream);
 
-/* Right-preconditioned restarted GMRES(restart) on K x = b with the same preconditioner: the fallback when
+/* Flexible (right-preconditioned) restarted GMRES(restart) on K x = b with the same preconditioner: the fallback when
  * the tangent is indefinite and CG reports GF_ERR_BREAKDOWN (the reference's LU still returns a Newton step
  * there, utils/opt_utils.py:176).  `iters` counts matrix-vector products. */
 typedef struct GfGmresWork {
   double* V;          /* [(restart+1)][n] Krylov basis                              */
-  double* z; double* t;  /* [n] each                                               */
+  double* Z;          /* [restart][n] preconditioned basis z_j = M^-1 v_j (flexible GMRES) */
+  double* t;          /* [n]                                                        */
   double* hdev;       /* [2*(restart+2)+1] device scalars                           */
   double* partial;    /* [1024*(restart+1)] per-CTA partial sums                    */
   double* h_host;     /* pinned host [2*(restart+2)+1]                              */

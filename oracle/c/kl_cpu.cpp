@@ -239,3 +239,125 @@ extern "C" int gfo_shell_assemble(const GfModel* m, int what, const GfShellOut* 
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Penalty coupling on the host (PENGoLINS transfer_penalty_residual[_deriv], GOLDFISH transfer_dRmdcpm_sub:
+// /root/reference/GOLDFISH/nonmatching_opt.py:745-752, 789-801, 864-867; utils/opt_utils.py:212-260): point
+// Hessians by forward-mode duals over penalty_point, then the same host-built destination lists as the CUDA
+// path (GfPenalty / GfPenaltyP with HOST pointers), OpenMP over evaluations / destinations.
+extern "C" int gfo_penalty_points(const GfModel* m, const GfPenalty* p, int with_X) {
+  const GfModel& M = *m; const GfPenalty& Q = *p;
+#pragma omp parallel for schedule(static)
+  for (int64_t ev = 0; ev < Q.n_eval; ++ev) {
+    double g[36];
+    for (int lane = 0; lane < 18; ++lane) {
+      const int side = lane / 9, kc = lane % 9, k = kc / 3, c = kc % 3;
+      const int32_t* conn = (side ? Q.connB : Q.connA) + ev * 16;
+      const double* bas = (side ? Q.basB : Q.basA) + ev * 48 + k * 16;
+      const int32_t* dd = (side ? Q.dofB : Q.dofA) + ev * 3;
+      const double* u = M.u + dd[0] + (size_t)c * dd[1] - dd[2];
+      double s = 0.0;
+      for (int a = 0; a < 16; ++a) s += bas[a] * u[conn[a]];
+      g[lane] = s;
+      const int blk = lane / 3;
+      const int32_t* cx; const double* bx;
+      if (blk == 0) { cx = Q.connC0 + ev * 16; bx = Q.basC0 + ev * 16; }
+      else if (blk == 1) { cx = Q.connC1 + ev * 16; bx = Q.basC1 + ev * 16; }
+      else if (blk < 4) { cx = Q.connA + ev * 16; bx = Q.basA + ev * 48 + (blk - 1) * 16; }
+      else { cx = Q.connB + ev * 16; bx = Q.basB + ev * 48 + (blk - 3) * 16; }
+      double x = 0.0;
+      for (int a = 0; a < 16; ++a) x += bx[a] * M.cp[(size_t)cx[a] * 4 + (lane % 3)];
+      g[18 + lane] = x;
+    }
+    const double tp[2] = {Q.tpar[ev * 2], Q.tpar[ev * 2 + 1]};
+    const double ad = Q.alpha[ev * 2], ar = Q.alpha[ev * 2 + 1];
+    for (int pass = 0; pass < (with_X ? 2 : 1); ++pass)
+      for (int d = 0; d < 18; ++d) {
+        Dual uv[18], Xv[18], grad[18], e;
+        for (int k = 0; k < 18; ++k) {
+          uv[k] = Dual(g[k], (pass == 0 && d == k) ? 1.0 : 0.0);
+          Xv[k] = Dual(g[18 + k], (pass == 1 && d == k) ? 1.0 : 0.0);
+        }
+        gf::penalty_point<Dual>(uv, Xv, tp, ad, ar, e, grad);
+        double* H = (pass == 0 ? Q.Huu : Q.HuX) + ev * 324;
+        for (int mm = 0; mm < 18; ++mm) H[mm * 18 + d] = grad[mm].d;
+        if (pass == 0 && d == 0) for (int mm = 0; mm < 18; ++mm) Q.g[ev * 18 + mm] = grad[mm].v;
+      }
+  }
+  return 0;
+}
+
+extern "C" int gfo_penalty_gather_R(const GfPenalty* p, double* R) {
+  const GfPenalty& Q = *p;
+#pragma omp parallel for schedule(static)
+  for (int64_t n = 0; n < Q.nR; ++n) {
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int64_t it = Q.R_ptr[n]; it < Q.R_ptr[n + 1]; ++it) {
+      const int32_t item = Q.R_item[it];
+      const int64_t ev = item >> 5;
+      const int ln = item & 31, side = ln >> 4, a = ln & 15;
+      const double* bas = (side ? Q.basB : Q.basA) + ev * 48;
+      const double* g = Q.g + ev * 18 + side * 9;
+      for (int k = 0; k < 3; ++k) for (int i = 0; i < 3; ++i) s[i] += bas[k * 16 + a] * g[3 * k + i];
+    }
+    for (int i = 0; i < 3; ++i) R[Q.R_row[n * 3 + i]] += s[i];
+  }
+  return 0;
+}
+
+extern "C" int gfo_penalty_gather_K(const GfPenalty* p, double* Kvals) {
+  const GfPenalty& Q = *p;
+#pragma omp parallel for schedule(static)
+  for (int64_t n = 0; n < Q.nK; ++n) {
+    double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t it = Q.K_ptr[n]; it < Q.K_ptr[n + 1]; ++it) {
+      const int32_t item = Q.K_item[it];
+      const int64_t ev = item >> 10;
+      const int la = (item >> 5) & 31, lb = item & 31;
+      const int sa = la >> 4, a = la & 15, sb = lb >> 4, b = lb & 15;
+      const double* bR = (sa ? Q.basB : Q.basA) + ev * 48;
+      const double* bC = (sb ? Q.basB : Q.basA) + ev * 48;
+      const double* H = Q.Huu + ev * 324 + (sa * 9) * 18 + sb * 9;
+      for (int k = 0; k < 3; ++k)
+        for (int l = 0; l < 3; ++l) {
+          const double w = bR[k * 16 + a] * bC[l * 16 + b];
+          for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) s[i * 3 + j] += w * H[(3 * k + i) * 18 + 3 * l + j];
+        }
+    }
+    for (int i = 0; i < 9; ++i) { const int64_t pos = Q.K_pos[n * 9 + i]; if (pos >= 0) Kvals[pos] += s[i]; }
+  }
+  return 0;
+}
+
+extern "C" int gfo_penalty_gather_P(const GfPenalty* p, const GfPenaltyP* pp) {
+  const GfPenalty& Q = *p; const GfPenaltyP& PP = *pp;
+#pragma omp parallel for schedule(static)
+  for (int64_t n = 0; n < PP.n_dest; ++n) {
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int64_t it = PP.ptr[n]; it < PP.ptr[n + 1]; ++it) {
+      const int64_t ev = PP.item_eval[it];
+      const int code = PP.item_code[it];
+      const int la = code & 31, xb = (code >> 5) & 7, lb = (code >> 8) & 15;
+      const int sa = la >> 4, a = la & 15;
+      const double* bR = (sa ? Q.basB : Q.basA) + ev * 48;
+      double cC;
+      if (xb == 0) cC = Q.basC0[ev * 16 + lb];
+      else if (xb == 1) cC = Q.basC1[ev * 16 + lb];
+      else if (xb < 4) cC = Q.basA[ev * 48 + (xb - 1) * 16 + lb];
+      else cC = Q.basB[ev * 48 + (xb - 3) * 16 + lb];
+      const double* H = Q.HuX + ev * 324 + (sa * 9) * 18 + xb * 3 + PP.field;
+      for (int k = 0; k < 3; ++k) { const double w = bR[k * 16 + a] * cC; for (int i = 0; i < 3; ++i) s[i] += w * H[(3 * k + i) * 18]; }
+    }
+    for (int i = 0; i < 3; ++i) { const int64_t pos = PP.pos[n * 3 + i]; if (pos >= 0) PP.vals[pos] = s[i]; }
+  }
+  return 0;
+}
+
+// K[bc rows / cols] were masked during scatter; write the unit diagonal (zeroRowsColumns, nonmatching_opt.py:693-700)
+extern "C" int gfo_bc_set_diag(const GfModel* m, double diag) {
+  for (int64_t i = 0; i < m->n_bc; ++i) {
+    const int64_t row = m->bc_list[i];
+    for (int64_t k = m->K.indptr[row]; k < m->K.indptr[row + 1]; ++k) m->K.vals[k] = (m->K.indices[k] == row) ? diag : 0.0;
+  }
+  return 0;
+}

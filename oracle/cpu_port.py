@@ -1,10 +1,13 @@
 """ORACLE / CPU BASELINE (test + measurement infrastructure) -- compiled CPU path.
 
-Drives oracle/c/kl_cpu.cpp (C++/OpenMP shell quadrature + CSR scatter, HOST
-memory) together with the numpy oracle's penalty terms and SuperLU solves: the
-"restated reference CPU path" timed by bench.py (`cpu_baseline`, `--impl
-reference`) with all host threads, and a second, independent CPU check of the
-numpy oracle at sizes the numpy AD cannot reach.
+Drives oracle/c/kl_cpu.cpp (C++/OpenMP shell quadrature, penalty coupling and CSR
+scatter, HOST memory) and oracle/c/mf_lu.cpp (multifrontal sparse LU on a nested
+dissection ordering, standing in for MUMPS): the "restated reference CPU path"
+timed by bench.py (`cpu_baseline`, `--impl reference`) with all host threads,
+and a second CPU check of the numpy oracle at sizes the numpy AD cannot reach.
+It shares the point-level header (goldfish_b200/csrc/kl_point.cuh, compiled for the
+host) with the CUDA kernels, so it is NOT an independent derivation; the numpy jet
+oracle (oracle/model.py) is, and tests/test_cpu_port.py holds this port to it.
 
 It reuses the product's plain-data model description (goldfish_b200.symbolic /
 _capi struct layouts are DATA, the arithmetic is oracle/c + oracle/model.py);
@@ -37,14 +40,15 @@ def _p(a):
 
 
 class CpuModel:
-    def __init__(self, problem, opt_field=(), shopt_surf_inds=(), with_penalty_oracle=True):
+    def __init__(self, problem, opt_field=(), shopt_surf_inds=(), with_penalty_oracle=False):
         if not os.path.exists(LIB):
             build()
         self.lib = C.CDLL(LIB)
         self.lib.gfo_shell_assemble.argtypes = [C.POINTER(capi.GfModel), C.c_int, C.POINTER(capi.GfShellOut)]
+        self.problem = problem
         self.S = S = Symbolic(problem, opt_field, shopt_surf_inds)
         self.opt_field, self.surf = list(opt_field), [list(x) for x in shopt_surf_inds]
-        self.om = OracleModel(problem) if with_penalty_oracle and S.pen["n_eval"] > 0 else None
+        self.om = None        # (the numpy oracle is only used by the tests that compare this port with it)
         a = self.a = {}
         descs = (capi.GfPatchDesc * len(S.patches))()
         for d, P in zip(descs, S.patches):
@@ -103,15 +107,53 @@ class CpuModel:
                 i = S.opt_field.index(f)
                 o.dWdP[f] = self.dWdP[i].ctypes.data; o.dVdP[f] = self.dVdP[i].ctypes.data
         self.o = o
+        self._build_penalty()
+        self._lu = None
+
+    # ------------------------------------------------------------------ penalty (compiled, oracle/c/kl_cpu.cpp)
+    def _build_penalty(self):
+        S = self.S
+        lib = self.lib
+        lib.gfo_penalty_points.argtypes = [C.POINTER(capi.GfModel), C.POINTER(capi.GfPenalty), C.c_int]
+        lib.gfo_penalty_gather_R.argtypes = [C.POINTER(capi.GfPenalty), C.c_void_p]
+        lib.gfo_penalty_gather_K.argtypes = [C.POINTER(capi.GfPenalty), C.c_void_p]
+        lib.gfo_penalty_gather_P.argtypes = [C.POINTER(capi.GfPenalty), C.POINTER(capi.GfPenaltyP)]
+        lib.gfo_bc_set_diag.argtypes = [C.POINTER(capi.GfModel), C.c_double]
+        pen = S.pen
+        q = capi.GfPenalty()
+        q.n_eval = pen["n_eval"]
+        self._pen_keep = {}
+        self.penP = [None for _ in S.opt_field]
+        if pen["n_eval"] > 0:
+            for k in ("connA", "connB", "connC0", "connC1", "basA", "basB", "basC0", "basC1", "tpar", "alpha",
+                      "dofA", "dofB", "R_ptr", "R_item", "R_row", "K_ptr", "K_item", "K_pos"):
+                a = np.ascontiguousarray(pen[k]); self._pen_keep[k] = a
+                setattr(q, k, _p(a) if a.size else C.c_void_p(0))
+            ne = pen["n_eval"]
+            self.pen_g, self.pen_Huu, self.pen_HuX = np.zeros(ne * 18), np.zeros(ne * 324), np.zeros(ne * 324)
+            q.g, q.Huu, q.HuX = _p(self.pen_g), _p(self.pen_Huu), _p(self.pen_HuX)
+            q.nR, q.nK = pen["nR"], pen["nK"]
+            for i, pp in enumerate(S.penP):
+                if pp.get("n_dest", 0) == 0:
+                    continue
+                vals = np.zeros(pp["nnz"])
+                s = capi.GfPenaltyP()
+                s.n_dest = pp["n_dest"]
+                arrs = [np.ascontiguousarray(pp[k]) for k in ("ptr", "item_eval", "item_code", "pos")]
+                s.ptr, s.item_eval, s.item_code, s.pos = [_p(a) for a in arrs]
+                s.vals, s.field = _p(vals), pp["field"]
+                M = sp.csr_matrix((vals, pp["indices"], pp["indptr"]), shape=(S.N, S.P_ncols[i]))
+                self.penP[i] = (M, s, arrs, vals)
+        self.pen = q
 
     def set_u(self, u):
         self.u[:] = u
-        if self.om is not None:
-            self.om.set_u(u)
 
-    def shell(self, what):
-        """Shell part through the compiled port: fills R / K / P / T / functionals in place."""
-        if what & capi.GF_OUT_R: self.R[:] = self.S.f_const
+    def assemble(self, what):
+        """Shells + coupling through the compiled port: R (BC rows zeroed), K (BCs applied, in the fixed
+        CSR pattern), P / penalty part of dR/dCP, T and the functionals -- all in place, all threads."""
+        S = self.S
+        if what & capi.GF_OUT_R: self.R[:] = S.f_const
         if what & capi.GF_OUT_K: self.Kv[:] = 0
         if what & capi.GF_OUT_P:
             for v in self.Pv + self.dWdP + self.dVdP: v[:] = 0
@@ -119,54 +161,116 @@ class CpuModel:
             self.Tv[:] = 0; self.dWdt[:] = 0; self.dVdt[:] = 0; self.dWdu[:] = 0; self.dt_el[:] = 0
         self.lib.gfo_shell_assemble(C.byref(self.m), what, C.byref(self.o))
         if what & capi.GF_OUT_T:
-            for P in self.S.patches:
+            for P in S.patches:
                 if P.th_kind == 0:
                     sl = self.dt_el[2 * P.el_off:2 * (P.el_off + P.nel)]
                     self.dWdt[P.th_off] += sl[0::2].sum(); self.dVdt[P.th_off] += sl[1::2].sum()
+        with_X = 1 if (what & capi.GF_OUT_P and S.opt_field) else 0
+        if S.pen["n_eval"] > 0 and (what & (capi.GF_OUT_R | capi.GF_OUT_K) or with_X):
+            self.lib.gfo_penalty_points(C.byref(self.m), C.byref(self.pen), with_X)
+            if what & capi.GF_OUT_R:
+                self.lib.gfo_penalty_gather_R(C.byref(self.pen), _p(self.R))
+            if what & capi.GF_OUT_K:
+                self.lib.gfo_penalty_gather_K(C.byref(self.pen), _p(self.Kv))
+            if with_X:
+                for pp in self.penP:
+                    if pp is not None:
+                        pp[3][:] = 0
+                        self.lib.gfo_penalty_gather_P(C.byref(self.pen), C.byref(pp[1]))
+        if what & capi.GF_OUT_R:
+            self.R[S.bc_list] = 0.0
+        if what & capi.GF_OUT_K:
+            self.lib.gfo_bc_set_diag(C.byref(self.m), 1.0)
+
+    shell = assemble        # older name
 
     def K_matrix(self):
+        """The assembled tangent (BCs applied) as scipy CSR sharing the value array."""
         S = self.S
-        K = sp.csr_matrix((self.Kv.copy(), self._idx["K"][1], self._idx["K"][0]), shape=(S.N, S.N))
-        if self.om is not None:
-            K = K + self.om.stiffness(apply_bcs=True, shell=False, penalty=True)   # BC rows/cols of the part are zeroed there
-        K = K.tolil(); bc = S.bc_list
-        K[bc, bc] = 1.0
-        return K.tocsr()
+        return sp.csr_matrix((self.Kv, self._idx["K"][1], self._idx["K"][0]), shape=(S.N, S.N))
 
     def residual(self):
-        R = self.R.copy()
-        if self.om is not None:
-            R += self.om.residual(apply_bcs=False, shell=False, penalty=True, const_loads=False)
-        R[self.S.bc_list] = 0.0
-        return R
+        return self.R.copy()
 
-    def iteration(self):
-        """One analysis + adjoint iteration of the restated reference CPU path (LU solves)."""
+    def P_matrix(self, i):
         S = self.S
+        Pm = sp.csr_matrix((self.Pv[i], self._idx["P"][i][1], self._idx["P"][i][0]), shape=(S.N, S.P_ncols[i]))
+        return Pm if self.penP[i] is None else Pm + self.penP[i][0]
+
+    def T_matrix(self):
+        S = self.S
+        return sp.csr_matrix((self.Tv, self._idx["T"][1], self._idx["T"][0]), shape=(S.N, S.n_th))
+
+    # ------------------------------------------------------------------ linear solves (multifrontal LU)
+    def direct_solver(self):
+        """Analysis phase (nested dissection + symbolic), once per pattern."""
+        if self._lu is None:
+            from .mf_solver import MultifrontalLU
+            S = self.S
+            n_s = S.n_scalar
+            rows, cols = [], []
+            for P in S.patches:
+                cand, mask, _ = S._own_stencil(P)
+                a, mm = np.nonzero(mask)
+                rows.append(P.cp_off + a); cols.append(P.cp_off + cand[a, mm])
+            if len(S.cpl_keys):
+                rows.append(S.cpl_keys // n_s); cols.append(S.cpl_keys % n_s)
+            r = np.concatenate(rows); c = np.concatenate(cols)
+            G = sp.csr_matrix((np.ones(len(r), dtype=np.int8), (r, c)), shape=(n_s, n_s)); G.sum_duplicates()
+            X = S.cp0[:, :3] / S.cp0[:, 3:4]
+            node_dofs = np.concatenate([np.stack([P.dof_off + f * P.ncp + np.arange(P.ncp) for f in range(3)], 1) for P in S.patches])
+            self._lu = MultifrontalLU(G, X, node_dofs, S.N)
+        return self._lu
+
+    def solve(self, b, transpose=False, refine=0):
+        """solve_Ax_b / solve_ATx_b (utils/opt_utils.py:156-209): a FRESH LU per call, the transposed system
+        re-factorised like the reference does (:199-204)."""
+        lu = self.direct_solver()
+        K = self.K_matrix()
+        if transpose:
+            KT = K.T.tocsr(); KT.sort_indices()            # explicit transpose, as the reference forms it
+            lu.factor(KT, K)
+            A = KT
+        else:
+            KT = K.T.tocsr(); KT.sort_indices()
+            lu.factor(K, KT)
+            A = K
+        x = lu.solve(b)
+        for _ in range(refine):
+            x = x + lu.solve(b - A @ x)
+        return x
+
+    def iteration(self, newton_rtol=1e-3, timings=None):
+        """One analysis + adjoint iteration of the restated reference CPU path: Newton from u = 0
+        (disp_imop.py:38-44) with an LU solve per step, W/V, linearisation (K, dR/dCP_f, dR/dt), adjoint
+        solve with the re-factorised transpose, total gradients."""
+        S = self.S
+        tm = timings if timings is not None else {}
         t0 = time.perf_counter()
+
+        def lap(name, t):
+            now = time.perf_counter(); tm[name] = tm.get(name, 0.0) + now - t; return now
         self.set_u(np.zeros(S.N))
         ref = None
+        t = t0
         for it in range(31):
-            self.shell(capi.GF_OUT_R | capi.GF_OUT_K)
-            R = self.residual()
-            nrm = np.linalg.norm(R); ref = nrm if it == 0 else ref
-            if it > 0 and nrm / ref < 1e-3:
+            self.assemble(capi.GF_OUT_R | capi.GF_OUT_K)
+            t = lap("assemble_RK", t)
+            nrm = np.linalg.norm(self.R); ref = nrm if it == 0 else ref
+            if it > 0 and nrm / ref < newton_rtol:
                 break
-            K = self.K_matrix()
-            self.set_u(self.u + spla.splu(K.tocsc()).solve(-R))
-        self.shell(capi.GF_OUT_K | capi.GF_OUT_W | capi.GF_OUT_P | capi.GF_OUT_T)
-        K = self.K_matrix()
+            du = self.solve(-self.R)
+            self.set_u(self.u + du)
+            t = lap("lu_state", t)
+        self.assemble(capi.GF_OUT_K | capi.GF_OUT_W | capi.GF_OUT_P | capi.GF_OUT_T)
+        t = lap("linearize", t)
         rhs = self.dWdu.copy(); rhs[S.bc_list] = 0.0
-        lam = spla.splu(K.T.tocsc()).solve(rhs)                      # re-factorised for the adjoint, as the reference does
-        grads = []
-        Ppen = self.om.dRdCP_fields(self.opt_field, self.surf[0], shell=False, penalty=True) if (self.om is not None and self.opt_field) else None
-        for i, f in enumerate(self.opt_field):
-            Pm = sp.csr_matrix((self.Pv[i], self._idx["P"][i][1], self._idx["P"][i][0]), shape=(S.N, S.P_ncols[i]))
-            g = self.dWdP[i] - Pm.T @ lam
-            if Ppen is not None:
-                g = g - Ppen[i].T @ lam
-            grads.append(g)
-        Tm = sp.csr_matrix((self.Tv, self._idx["T"][1], self._idx["T"][0]), shape=(S.N, S.n_th))
-        grads.append(self.dWdt - Tm.T @ lam)
+        lam = self.solve(rhs, transpose=True)
+        t = lap("lu_adjoint", t)
+        grads = [self.dWdP[i] - self.P_matrix(i).T @ lam for i in range(len(self.opt_field))]
+        grads.append(self.dWdt - self.T_matrix().T @ lam)
+        t = lap("gradients", t)
         self.newton_its = it
+        self.lam = lam
+        self.W, self.V = self.WV[0::2].sum(), self.WV[1::2].sum()
         return time.perf_counter() - t0, grads

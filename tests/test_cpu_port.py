@@ -1,6 +1,7 @@
-"""CPU: the compiled C++/OpenMP port (oracle/c/kl_cpu.cpp) agrees with the numpy
-oracle -- two independent CPU restatements (jets vs. dual numbers over the
-hand-derived first variation) of the same shell quadrature."""
+"""CPU: the compiled C++/OpenMP port (oracle/c/kl_cpu.cpp: shells + penalty coupling; oracle/c/mf_lu.cpp:
+multifrontal LU) agrees with the numpy oracle (second-order jets of one energy expression).  The port shares the
+point-level header with the CUDA kernels (dual numbers over a hand-derived first variation), so the numpy oracle is
+the independent derivation and this file is what ties the port -- bench.py's CPU arm -- to it."""
 import numpy as np
 import scipy.sparse as sp
 import pytest
@@ -17,20 +18,59 @@ def test_port_matches_numpy_oracle(case):
     om = OracleModel(pr)
     u = cases.random_state(om.N, om.bc_global)
     cm.set_u(u); om.set_u(u)
-    cm.shell(capi.GF_OUT_R | capi.GF_OUT_K | capi.GF_OUT_W | capi.GF_OUT_P | capi.GF_OUT_T)
+    cm.assemble(capi.GF_OUT_R | capi.GF_OUT_K | capi.GF_OUT_W | capi.GF_OUT_P | capi.GF_OUT_T)
     rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
-    assert rel(cm.residual(), om.residual()) < 1e-11
+    assert rel(cm.residual(), om.residual()) < 1e-11                # shells + penalty + BCs, all from the port
     K = cm.K_matrix(); Ko = om.stiffness()
+    assert np.array_equal(K.indptr, Ko.indptr) and np.array_equal(K.indices, Ko.indices)
     assert abs(K - Ko).max() < 1e-11 * abs(Ko).max()
-    T = sp.csr_matrix((cm.Tv, cm._idx["T"][1], cm._idx["T"][0]), shape=(om.N, om.n_th))
+    T = cm.T_matrix()
     assert abs(T - om.dRdt()).max() < 1e-11 * abs(om.dRdt()).max()
     assert abs(cm.WV[0::2].sum() - om.energy()) < 1e-11 * om.energy()
     assert rel(cm.dWdt, om.dWdt()) < 1e-11 and rel(cm.dVdt, om.dVdt()) < 1e-11
     for i, f in enumerate(kw["opt_field"]):
-        Psh = sp.csr_matrix((cm.Pv[i], cm._idx["P"][i][1], cm._idx["P"][i][0]), shape=(om.N, cm.S.P_ncols[i]))
-        Ao = om.dRdCP_fields([f], kw["shopt_surf_inds"][i], penalty=False)[0]
-        assert abs(Psh - Ao).max() < 1e-11 * abs(Ao).max()
+        Ao = om.dRdCP(f, kw["shopt_surf_inds"][i])                  # shell + penalty parts
+        assert abs(cm.P_matrix(i) - Ao).max() < 1e-11 * abs(Ao).max()
         assert rel(cm.dWdP[i], om.dWdCP(f, kw["shopt_surf_inds"][i])) < 1e-11
+
+
+def test_port_iteration_matches_numpy_oracle():
+    """One full analysis + adjoint iteration (Newton with multifrontal LU, re-factorised transpose for the
+    adjoint, total gradients) against the numpy oracle with SuperLU."""
+    pr, kw = cases.tbeam_small()
+    cm = CpuModel(pr, **kw)
+    om = OracleModel(pr)
+    _, grads = cm.iteration()
+    uo = om.solve_nonlinear(max_it=30, rtol=1e-3)
+    assert cm.newton_its == len(om.newton_history) - 1
+    assert np.linalg.norm(cm.u - uo) < 1e-9 * np.linalg.norm(uo)
+    lam = om.solve(om.stiffness(), om.dWdu(apply_bcs=True), transpose=True)
+    assert np.linalg.norm(cm.lam - lam) < 1e-8 * np.linalg.norm(lam)
+    go = om.dWdt() - om.dRdt().T @ lam
+    assert np.linalg.norm(grads[-1] - go) < 1e-8 * np.linalg.norm(go)
+    for i, f in enumerate(kw["opt_field"]):
+        gp = om.dWdCP(f, kw["shopt_surf_inds"][i]) - om.dRdCP(f, kw["shopt_surf_inds"][i]).T @ lam
+        assert np.linalg.norm(grads[i] - gp) < 1e-8 * np.linalg.norm(gp)
+
+
+def test_multifrontal_lu_matches_superlu():
+    """oracle/c/mf_lu.cpp on the tangent pattern of a non-matching 8-patch cylinder with random UNSYMMETRIC values
+    (the LU, not a Cholesky, is what the reference's MUMPS run does) against scipy's SuperLU."""
+    import scipy.sparse.linalg as spla
+    from goldfish_b200 import problems
+    cm = CpuModel(problems.cylinder(n_el=10))
+    S = cm.S
+    lu = cm.direct_solver()
+    rng = np.random.default_rng(0)
+    A = sp.csr_matrix((rng.standard_normal(len(S.K_indices)), S.K_indices, S.K_indptr), shape=(S.N, S.N)) + sp.diags(np.full(S.N, 300.0))
+    A = A.tocsr(); A.sort_indices()
+    AT = A.T.tocsr(); AT.sort_indices()
+    b = rng.standard_normal(S.N)
+    x = lu.factor(A, AT).solve(b)
+    assert np.linalg.norm(A @ x - b) < 1e-12 * np.linalg.norm(b)
+    xs = spla.splu(A.tocsc()).solve(b)
+    assert np.linalg.norm(x - xs) < 1e-11 * np.linalg.norm(xs)
+    assert lu.nfronts > 10 and lu.flops > 0
 
 
 # ---- known answers on closed, multi-patch, non-matching NURBS cylinders (through the compiled port) ----
@@ -58,15 +98,16 @@ def _solve_linear_port(pr):
     import scipy.sparse.linalg as spla
     cm = CpuModel(pr)
     cm.set_u(np.zeros(cm.S.N))
-    cm.shell(capi.GF_OUT_R | capi.GF_OUT_K)
-    return cm, spla.splu(cm.K_matrix().tocsc()).solve(-cm.residual())
+    cm.assemble(capi.GF_OUT_R | capi.GF_OUT_K)
+    return cm, cm.solve(-cm.residual())
 
 
 def _radial_approach(cm, u, probes):
     from oracle import bspline as obs
     tot = 0.0
+    om = OracleModel(cm.problem)
     for s, xi, er in probes:
-        P = cm.om.patches[s]
+        P = om.patches[s]
         conn, D = obs.surface_basis(P.ku, P.kv, 3, 3, P.cp[:, 3], np.array([xi]))
         tot -= sum(er[f] * (D[0, 0] * u[P.off + f * P.ncp + conn[0]]).sum() for f in range(2))
     return tot

@@ -94,7 +94,7 @@ def test_baseline_configs_match_goldens(DM, case, gold):
     # C1's tangent has kappa_1 ~ 1.5e12; the golden's LU solves are iteratively refined with an extended-precision
     # residual (tests/golden/make_oracle_goldens.py) and DeviceModel.solve refines on the TRUE residual, so both
     # configurations are held to north_star's 1e-8.
-    assert dm.last_true_relres is not None and dm.last_true_relres < 1e-9
+    assert dm.last_true_relres is not None and dm.last_true_relres < 1e-8
     assert np.linalg.norm(lam.cpu().numpy() - g["lam"]) < TOL_SOL * np.linalg.norm(g["lam"])
     assert np.linalg.norm(tot.cpu().numpy() - g["dWdt_total"]) < TOL_SOL * np.linalg.norm(g["dWdt_total"])
 
