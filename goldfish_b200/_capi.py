@@ -85,7 +85,8 @@ class GfDist(C.Structure):
 
 class GfPrecond(C.Structure):
     _fields_ = [("fine", C.POINTER(GfSchwarz)), ("coarse", C.POINTER(GfSchwarz)), ("P", GfCsr), ("Rt", GfCsr),
-                ("rc", c_vp), ("zc", c_vp), ("bc_c", c_vp), ("n_bc_c", c_i64), ("dist", C.POINTER(GfDist))]
+                ("rc", c_vp), ("zc", c_vp), ("bc_c", c_vp), ("n_bc_c", c_i64), ("dist", C.POINTER(GfDist)),
+                ("cinv", c_vp), ("cinv_row0", c_i64), ("cinv_rows", c_i64)]
 
 
 class GfNodeRows(C.Structure):
@@ -103,7 +104,7 @@ class GfGmresWork(C.Structure):
 
 # (struct, last field) in the order of gf_abi_layout's ids
 ABI_STRUCTS = [(GfPatchDesc, "f"), (GfCsr, "vals"), (GfModel, "T"), (GfShellOut, "dt_el"), (GfPenalty, "K_pos"),
-               (GfPenaltyP, "field"), (GfCsrT, "perm"), (GfSchwarz, "flag"), (GfDist, "comm"), (GfPrecond, "dist"),
+               (GfPenaltyP, "field"), (GfCsrT, "perm"), (GfSchwarz, "flag"), (GfDist, "comm"), (GfPrecond, "cinv_rows"),
                (GfPcgWork, "nodes"), (GfGmresWork, "nodes")]
 
 

@@ -42,7 +42,7 @@ extern "C" int gf_abi_layout(int which, int64_t* size, int64_t* last_offset) {
     case 6: GF_LAYOUT(GfCsrT, perm);
     case 7: GF_LAYOUT(GfSchwarz, flag);
     case 8: GF_LAYOUT(GfDist, comm);
-    case 9: GF_LAYOUT(GfPrecond, dist);
+    case 9: GF_LAYOUT(GfPrecond, cinv_rows);
     case 10: GF_LAYOUT(GfPcgWork, nodes);
     case 11: GF_LAYOUT(GfGmresWork, nodes);
     default: return gf::set_error(GF_ERR_BADARG, "gf_abi_layout: unknown struct id");

@@ -450,8 +450,60 @@ static int apply_A(const GfCsr& A, const GfDist* dist, const GfNodeRows* nodes, 
 }
 }  // namespace gf
 
+namespace gf {
+// y[row] = A[row, :] . x for a dense row-major FP64 slab: one warp per row, 128-bit loads, x through the read-only
+// path (it is a few hundred kB and stays in L2).  HBM-bound: 8 bytes per entry, read once.
+__global__ void __launch_bounds__(256)
+k_dense_rows(const double* __restrict__ A, int64_t rows, int64_t ncols, const double* __restrict__ x, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n2 = ncols >> 1;
+  for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += nwarps) {
+    const double* a = A + row * ncols;
+    double s0 = 0.0, s1 = 0.0;
+    if ((((uintptr_t)a) & 15) == 0) {
+      const double2* a2 = reinterpret_cast<const double2*>(a);
+      const double2* x2 = reinterpret_cast<const double2*>(x);
+      int64_t k = lane;
+      for (; k + 96 < n2; k += 128) {
+        const double2 v0 = __ldcs(a2 + k), v1 = __ldcs(a2 + k + 32), v2 = __ldcs(a2 + k + 64), v3 = __ldcs(a2 + k + 96);
+        const double2 w0 = __ldg(x2 + k), w1 = __ldg(x2 + k + 32), w2 = __ldg(x2 + k + 64), w3 = __ldg(x2 + k + 96);
+        s0 = fma(v0.x, w0.x, s0); s1 = fma(v0.y, w0.y, s1); s0 = fma(v1.x, w1.x, s0); s1 = fma(v1.y, w1.y, s1);
+        s0 = fma(v2.x, w2.x, s0); s1 = fma(v2.y, w2.y, s1); s0 = fma(v3.x, w3.x, s0); s1 = fma(v3.y, w3.y, s1);
+      }
+      for (; k < n2; k += 32) { const double2 v = __ldcs(a2 + k); const double2 w = __ldg(x2 + k); s0 = fma(v.x, w.x, s0); s1 = fma(v.y, w.y, s1); }
+      if ((ncols & 1) && lane == 0) s0 = fma(a[ncols - 1], x[ncols - 1], s0);
+    } else {
+      for (int64_t k = lane; k < ncols; k += 32) s0 = fma(a[k], __ldg(x + k), s0);
+    }
+    const double s = warp_sum(s0 + s1);
+    if (lane == 0) y[row] = s;
+  }
+}
+}  // namespace gf
+
 extern "C" int gf_precond_apply(const GfPrecond* pc, const double* r, double* z, int64_t n, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (pc->cinv) {
+    // sharded two-level: restriction (replicated), own row slab of Kc^-1 r_c, own fine blocks, prolongation of the
+    // slab, ONE all-reduce for both levels
+    const int64_t nc = pc->Rt.nrows;
+    int rc = gf_spmv(&pc->Rt, r, pc->rc, 1.0, 0.0, st);
+    if (rc) return rc;
+    if (pc->n_bc_c > 0) { k_zero_list<<<vec_grid(pc->n_bc_c), RED_THREADS, 0, st>>>(pc->bc_c, pc->n_bc_c, pc->rc); count_launch(1); }
+    cudaError_t e = cudaMemsetAsync(pc->zc, 0, (size_t)nc * sizeof(double), st);
+    if (e != cudaSuccess) return set_cuda_error(e, "gf_precond_apply memset");
+    if (pc->cinv_rows > 0) {
+      int64_t g = (pc->cinv_rows * 32 + 255) / 256; if (g > 148 * 8) g = 148 * 8;
+      k_dense_rows<<<(unsigned)g, 256, 0, st>>>(pc->cinv, pc->cinv_rows, nc, pc->rc, pc->zc + pc->cinv_row0);
+      count_launch(1);
+    }
+    rc = gf_schwarz_apply(pc->fine, r, z, n, st);
+    if (rc) return rc;
+    rc = gf_spmv(&pc->P, pc->zc, z, 1.0, 1.0, st);             // z += P z_c[slab]
+    if (rc) return rc;
+    return dist_allreduce(pc->dist, z, n, st);
+  }
   if (!pc->coarse) {
     int rc0 = gf_schwarz_apply(pc->fine, r, z, n, st);
     if (rc0 == 0 && pc->dist && pc->dist->n_ranges > 0) rc0 = dist_allreduce(pc->dist, z, n, st);

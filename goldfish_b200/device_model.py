@@ -90,7 +90,7 @@ class DeviceCsr:
 
 class DeviceModel:
     def __init__(self, problem, opt_field=(), shopt_surf_inds=(), device=None, symbolic=None,
-                 precond="schwarz", schwarz_layers=2, coarse_nc="auto", schwarz_sub=(24, 96), distributed=None):
+                 precond="schwarz", schwarz_layers=2, coarse_nc="auto", schwarz_sub="auto", distributed=None):
         if not torch.cuda.is_available():
             raise capi.GoldfishError("goldfish_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = capi.load()
@@ -197,6 +197,16 @@ class DeviceModel:
         self.precond = precond
         self.schwarz_layers = schwarz_layers
         self.schwarz_sub = schwarz_sub
+        if schwarz_sub == "auto":
+            # one CTA sweeps one sub-domain, and the sweep is a latency chain whose length grows with the block: keep
+            # at least ~one wave (148 SMs) of blocks per GPU by shrinking the sub-domains as the ranks multiply
+            from .schwarz import SchwarzSetup as _SS
+            self.schwarz_sub = (24, 96)           # measured best on one B200 at 1 M dofs (profiles/r1_sweep_tuning_*.jsonl)
+            if self.world > 1:
+                for cand in ((24, 96), (24, 48), (24, 24), (12, 24)):
+                    self.schwarz_sub = cand
+                    if _SS.count_subdomains(S.patches, cand) >= 148 * self.world:
+                        break
         import os as _os0
         if _os0.environ.get("GF_SW_SUB"):                  # tuning experiments: "48" or "24,96"
             v = [int(x) for x in _os0.environ["GF_SW_SUB"].split(",")]
@@ -208,8 +218,12 @@ class DeviceModel:
             # the coarse sweeps run beside the fine ones: keep their chain shorter than the fine chains
             # (which shrink per GPU when the blocks are spread over several ranks)
             # (thread-block-cluster coarse sweeps: ~1.8 us per block step measured on B200)
-            cap_nc = 28 if self.world < 2 else (20 if self.world < 4 else 16)
-            coarse_nc = 0 if max_ne < 16 else int(min(cap_nc, max(8, max_ne // 7)))
+            coarse_nc = 0 if max_ne < 16 else int(min(28, max(8, max_ne // 7)))
+            if self.world > 1:
+                # sharded: the coarse solve is a dense product with a row slab of Kc^-1 (no chain to keep short), so
+                # the level does not shrink with the GPU count; bound the dense inverse to ~48 k coarse dofs
+                while coarse_nc > 8 and 3 * len(S.patches) * (coarse_nc + 3) ** 2 > 48000:
+                    coarse_nc -= 1
         self.coarse_nc = int(coarse_nc) if precond == "schwarz" else 0
         self.problem = problem
         self._pc = None
@@ -502,7 +516,8 @@ class DeviceModel:
                 Rd.vals.copy_(torch.from_numpy(Rt.data))
                 rc = torch.zeros(P.shape[1], dtype=torch.float64, device=self.device)
                 zc = torch.zeros(P.shape[1], dtype=torch.float64, device=self.device)
-                pc.coarse = C.pointer(cm._schwarz())
+                if self.dist is None:
+                    pc.coarse = C.pointer(cm._schwarz())
                 pc.P, pc.Rt = Pd.c_struct(), Rd.c_struct()
                 pc.rc, pc.zc = _ptr(rc), _ptr(zc)
                 pc.bc_c, pc.n_bc_c = _ptr(cm.t["bc_list"]), len(cm.sym.bc_list)
@@ -584,6 +599,27 @@ class DeviceModel:
         capi.check(rc, "gf_gmres")
         return its.value, rel.value
 
+    def _dense_coarse_inverse(self, cm, pc):
+        """Sharded runs: this rank's row slab of Kc^-1 (FP64).  One-off set-up per coarse refresh, done with the
+        dense Cholesky of the library stack (cuSOLVER through torch) -- plumbing, not the hot path: every Krylov
+        iteration then applies the slab with the hand-written k_dense_rows product (GfPrecond.cinv)."""
+        nc = cm.sym.N
+        Kc = cm.K
+        rows = torch.repeat_interleave(torch.arange(nc, device=self.device), torch.from_numpy(np.diff(Kc.indptr_h)).to(self.device))
+        D = torch.zeros((nc, nc), dtype=torch.float64, device=self.device)
+        D.index_put_((rows, Kc.indices.long()), Kc.vals[:Kc.nnz], accumulate=True)
+        del rows
+        D = 0.5 * (D + D.T)
+        L = torch.linalg.cholesky(D)
+        del D
+        inv = torch.cholesky_inverse(L)
+        del L
+        r0 = (nc * self.rank) // self.world; r1 = (nc * (self.rank + 1)) // self.world
+        self._cinv = inv[r0:r1].contiguous().clone()
+        del inv
+        torch.cuda.empty_cache()
+        pc.cinv, pc.cinv_row0, pc.cinv_rows = _ptr(self._cinv), r0, r1 - r0
+
     def refresh_coarse(self):
         """Re-assemble and re-factor the coarse level at the next preconditioner set-up."""
         self._coarse_factored = False
@@ -617,8 +653,11 @@ class DeviceModel:
                 # (refresh_coarse() forces a rebuild).
                 cm = self._coarse[0]
                 cm.assemble(tangent=True)
-                capi.check(self.lib.gf_schwarz_factor(C.byref(cm._schwarz()), C.byref(cm.K.c_struct()), st),
-                           "gf_schwarz_factor(coarse)")
+                if self.dist is None:
+                    capi.check(self.lib.gf_schwarz_factor(C.byref(cm._schwarz()), C.byref(cm.K.c_struct()), st),
+                               "gf_schwarz_factor(coarse)")
+                else:
+                    self._dense_coarse_inverse(cm, pc)
                 self._coarse_factored = True
         capi.check(self.lib.gf_jacobi_setup(C.byref(cs), _ptr(self.w_dinv), st), "gf_jacobi_setup")
         self._sw_factored = True

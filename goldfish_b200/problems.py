@@ -10,6 +10,7 @@ intersections with their mortar parametric coordinates.
   plate()          /root/reference/demos_csdl_alpha/thickness_opt/plate_const_th_opt_wint.py:12-150
                    (BASELINE C1; geometry + intersection tables from tests/golden/plate_c1_input.npz)
   cylinder()       synthetic 8-patch non-matching cylinder (BASELINE C3)
+  wingbox()        synthetic 40-patch wing box with T- and X-junction intersections (BASELINE C4)
 
 Layout conventions: scalar CP index a = i + j*n_u; patch-local vector dof
 = field*n_cp + a; global dofs = patches concatenated in list order
@@ -200,6 +201,80 @@ def cylinder(n_el=32, p=3, n_circ=4, n_axial=2, R=1.0, L=4.0, E=68e9, nu=0.35, h
     return dict(name=f"cylinder_{n_circ}x{n_axial}_ne{n_el}", patches=patches, E=E, nu=nu,
                 interfaces=interfaces, penalty_coefficient=penalty_coefficient, point_loads=[],
                 edge_loads=[])
+
+
+def wingbox(h=0.05, n_seg=10, n_spar=3, n_rib=17, L=10.0, C=2.0, H=0.4, p=3, E=68e9, nu=0.35, h_th=1.0e-2,
+            penalty_coefficient=1.0e3, pressure=-1.0e3, quad_deg_const=3, thickness_kind="const", target_dofs=None):
+    """Synthetic wing-box-like shell (BASELINE configs[3], SURVEY.md section 8d "C4"): a rectangular box beam of
+    span L (x), chord C (y) and height H (z) made of
+      2 skins x n_seg spanwise segments  (segments meet edge to edge),
+      n_spar full-span spars             (top / bottom edges lie INSIDE every skin segment: T-junctions),
+      n_rib ribs between the outer spars (edges inside a skin segment and on the outer spars: T-junctions;
+                                          the inner spars pass through the rib interior: X-junctions),
+    i.e. 2 n_seg + n_spar + n_rib non-matching bicubic patches (40 by default) and
+    2 (n_seg - 1) + 2 n_spar n_seg + 2 n_rib + n_rib n_spar intersections (163), most of them interior to at least
+    one patch -- the situation of the reference's wing models (demos_csdl_alpha/ex_caddee/wing_int_data.npz: 93 of
+    124 interface sides in a patch interior).  Every patch has its own element size (h scaled by 1 + 0.04 (s mod 6))
+    so no two meshes match.  Root (x = 0) clamped with two CP layers, dead pressure on the upper skin.
+    target_dofs: choose h so that the model has about that many displacement dofs."""
+    if target_dofs is not None:
+        area = 2 * L * C + n_spar * L * H + n_rib * 0.8 * C * H
+        h = float(np.sqrt(3.0 * area / target_dofs)) * 1.04
+    xs = np.linspace(0.0, L, n_seg + 1)
+    y_sp = np.linspace(0.1 * C, 0.9 * C, n_spar) if n_spar > 1 else np.array([0.5 * C])
+    ya, yb = float(y_sp[0]), float(y_sp[-1])
+    # rib stations: evenly spread, nudged away from the segment boundaries
+    x_rib = (np.arange(n_rib) + 0.37) * L / n_rib
+    for r in range(n_rib):
+        d = np.abs(xs - x_rib[r])
+        if d.min() < 0.08 * L / n_seg:
+            x_rib[r] += 0.13 * L / n_seg
+    th = dict(kind=thickness_kind, values=h_th)
+    patches, meta = [], []          # meta: (kind, index data, n_el0, n_el1)
+
+    def add(pts, Lu, Lv, bc, load):
+        s = len(patches)
+        hs = h * (1.0 + 0.04 * (s % 6))
+        n0 = max(4, int(np.ceil(Lu / hs))); n1 = max(4, int(np.ceil(Lv / hs)))
+        srf = _ruled_quad(pts, n0, n1, p)
+        patches.append(_patch_from_surface(srf, quad_deg_const * p, th, bc, load))
+        meta.append((n0, n1))
+        return s
+    clamp = [(f, 0, 0, 2) for f in range(3)]
+    skin = {}
+    for side, z in (("lo", 0.0), ("up", H)):
+        for k in range(n_seg):
+            pts = [[xs[k], 0, z], [xs[k + 1], 0, z], [xs[k], C, z], [xs[k + 1], C, z]]
+            skin[side, k] = add(pts, xs[k + 1] - xs[k], C, clamp if k == 0 else [], (0.0, 0.0, pressure) if side == "up" else (0.0, 0.0, 0.0))
+    spar = [add([[0, y, 0], [L, y, 0], [0, y, H], [L, y, H]], L, H, clamp, (0.0, 0.0, 0.0)) for y in y_sp]
+    rib = [add([[x, ya, 0], [x, yb, 0], [x, ya, H], [x, yb, H]], yb - ya, H, [], (0.0, 0.0, 0.0)) for x in x_rib]
+    interfaces = []
+
+    def itf(a, endsA, b, endsB, nA, nB):
+        n_m = 2 * max(nA, nB, 2)
+        interfaces.append(dict(patches=(a, b), xi=(mortar_coords(endsA, n_m), mortar_coords(endsB, n_m))))
+    for side in ("lo", "up"):
+        v_edge = 0.0 if side == "lo" else 1.0
+        for k in range(n_seg - 1):                                   # skin segment | skin segment
+            a, b = skin[side, k], skin[side, k + 1]
+            itf(a, [[1., 0.], [1., 1.]], b, [[0., 0.], [0., 1.]], meta[a][1], meta[b][1])
+        for j, y in enumerate(y_sp):                                 # spar edge on the inside of every skin segment
+            for k in range(n_seg):
+                a, b = skin[side, k], spar[j]
+                itf(a, [[0., y / C], [1., y / C]], b, [[xs[k] / L, v_edge], [xs[k + 1] / L, v_edge]],
+                    meta[a][0], int(np.ceil(meta[b][0] / n_seg)))
+        for r, x in enumerate(x_rib):                                # rib edge on the inside of one skin segment
+            k = int(np.searchsorted(xs, x) - 1)
+            a, b = skin[side, k], rib[r]
+            u = (x - xs[k]) / (xs[k + 1] - xs[k])
+            itf(a, [[u, ya / C], [u, yb / C]], b, [[0., v_edge], [1., v_edge]], int(np.ceil(meta[a][1] * (yb - ya) / C)), meta[b][0])
+    for r, x in enumerate(x_rib):                                    # rib | spar (vertical lines)
+        for j, y in enumerate(y_sp):
+            a, b = spar[j], rib[r]
+            ur = (y - ya) / (yb - ya) if yb > ya else 0.5
+            itf(a, [[x / L, 0.], [x / L, 1.]], b, [[ur, 0.], [ur, 1.]], meta[a][1], meta[b][1])
+    return dict(name=f"wingbox_{len(patches)}p_h{h:.4g}", patches=patches, E=E, nu=nu, interfaces=interfaces,
+                penalty_coefficient=penalty_coefficient, point_loads=[], edge_loads=[])
 
 
 def num_dofs(problem):

@@ -94,6 +94,11 @@ class SchwarzSetup:
         self.blocks = [b for b, m in zip(self.blocks, mask) if m]
 
     @staticmethod
+    def count_subdomains(patches, sub):
+        sub_u, sub_v = (sub, sub) if np.isscalar(sub) else sub
+        return int(sum(max(1, int(np.ceil(P.n_u / sub_u))) * max(1, int(np.ceil(P.n_v / sub_v))) for P in patches))
+
+    @staticmethod
     def _subdomains(patches, sub):
         """Rectangles (i0, i1, j0, j1) of at most sub x sub (or sub[0] x sub[1]) control points tiling each patch."""
         sub_u, sub_v = (sub, sub) if np.isscalar(sub) else sub

@@ -254,6 +254,13 @@ typedef struct GfPrecond {
   const int32_t* bc_c;            /* coarse zero-dofs                                 */
   int64_t n_bc_c;
   const GfDist* dist;             /* NULL or n_ranges == 0: single process            */
+  /* Sharded runs: the coarse solve as a dense product.  Every rank holds a ROW SLAB of the (symmetric) inverse of
+   * the coarse operator, FP64 row-major [cinv_rows][Nc]; it computes z_c[slab] = Kc^-1[slab, :] r_c, prolongates
+   * only that part, and the all-reduce that already sums the fine-block contributions completes z.  A 2 * n_blockrows
+   * latency chain (k_sw_coarse_cluster, replicated on every GPU) becomes an HBM-bound product split over the GPUs
+   * with no extra exchange step.  NULL: band factor `coarse` (single-GPU path). */
+  const double* cinv;
+  int64_t cinv_row0, cinv_rows;
 } GfPrecond;
 int gf_precond_apply(const GfPrecond* pc, const double* r, double* z, int64_t n, void* stream);
 

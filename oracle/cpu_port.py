@@ -240,7 +240,7 @@ class CpuModel:
             x = x + lu.solve(b - A @ x)
         return x
 
-    def iteration(self, newton_rtol=1e-3, timings=None):
+    def iteration(self, newton_rtol=1e-3, timings=None, refine=0):
         """One analysis + adjoint iteration of the restated reference CPU path: Newton from u = 0
         (disp_imop.py:38-44) with an LU solve per step, W/V, linearisation (K, dR/dCP_f, dR/dt), adjoint
         solve with the re-factorised transpose, total gradients."""
@@ -259,13 +259,13 @@ class CpuModel:
             nrm = np.linalg.norm(self.R); ref = nrm if it == 0 else ref
             if it > 0 and nrm / ref < newton_rtol:
                 break
-            du = self.solve(-self.R)
+            du = self.solve(-self.R, refine=refine)
             self.set_u(self.u + du)
             t = lap("lu_state", t)
         self.assemble(capi.GF_OUT_K | capi.GF_OUT_W | capi.GF_OUT_P | capi.GF_OUT_T)
         t = lap("linearize", t)
         rhs = self.dWdu.copy(); rhs[S.bc_list] = 0.0
-        lam = self.solve(rhs, transpose=True)
+        lam = self.solve(rhs, transpose=True, refine=refine)
         t = lap("lu_adjoint", t)
         grads = [self.dWdP[i] - self.P_matrix(i).T @ lam for i in range(len(self.opt_field))]
         grads.append(self.dWdt - self.T_matrix().T @ lam)

@@ -202,8 +202,9 @@ def test_patch_sharded_two_gpus_match_single_gpu():
     import json
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT ")][0][7:])
     assert max(res["u"], res["lam"], res["gT"], res["gP"]) < 1e-7
-    # same preconditioner, all-reduce changes the summation order: counts agree up to the check interval
-    assert all(abs(a - b) <= 10 for a, b in zip(res["its_sharded"], res["its_single"]))
+    # the sharded preconditioner differs on purpose (smaller sub-domains per GPU, dense coarse solve split over the
+    # ranks): iteration counts stay in the same range, they need not be equal
+    assert all(a <= 2 * b + 20 for a, b in zip(res["its_sharded"], res["its_single"]))
 
 
 def test_pinched_ring_known_answer_on_gpu(DM):
