@@ -40,7 +40,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-el", type=int, default=int(os.environ.get("GF_BENCH_NEL", "201")),
                     help="elements per patch side; 201 = BASELINE configs[2] (8 patches, ~1.03 M DOF)")
-    ap.add_argument("--topology", default="4x2", help="patches around x along the cylinder (4x2 = BASELINE configs[2]; 8x5 = 40 patches)")
+    ap.add_argument("--topology", default="4x2", help="patches around x along the cylinder (4x2 = BASELINE configs[2]), or "
+                    "'wingbox' = BASELINE configs[3] (40 patches, --dofs sets the size)")
+    ap.add_argument("--dofs", type=float, default=1.0e7, help="--topology wingbox: target number of displacement dofs")
     ap.add_argument("--cpu-n-el", type=int, default=64, help="mesh of the bounded cpu_baseline sample in our arm's line")
     ap.add_argument("--no-trend", action="store_true", help="--impl reference: skip the three smaller meshes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -49,11 +51,17 @@ def parse():
 
 
 def topo(args):
+    if args.topology.lower() == "wingbox":
+        return ("wingbox", float(args.dofs))
     a, b = args.topology.lower().split("x")
     return int(a), int(b)
 
 
 def workload_name(n_el, n_circ=4, n_axial=2):
+    if n_circ == "wingbox":
+        return ("wingbox_40p_%.3gM: synthetic wing box (BASELINE configs[3]): 2 skins x 10 segments + 3 spars + 17 ribs = 40 non-matching "
+                "bicubic patches, 163 intersections (T- and X-junctions interior to the patches), shape fields 0,1,2 + per-patch thickness"
+                % (n_axial / 1e6))
     if (n_circ, n_axial) == (4, 2):
         return ("cylinder_4x2_ne%d: synthetic 8-patch non-matching bicubic NURBS cylinder (BASELINE configs[2]), 12 intersections, "
                 "shape fields 0,1,2 + per-patch thickness" % n_el)
@@ -66,6 +74,9 @@ def workload(n_el, n_circ=4, n_axial=2):
     """BASELINE configs[2] (default 4 x 2 patches); --topology 8x5 gives the 40-patch, 72-intersection stand-in for
     configs[3] (n_el 286 there is ~10 M DOF)."""
     from goldfish_b200 import problems
+    if n_circ == "wingbox":
+        pr = problems.wingbox(target_dofs=n_axial)
+        return pr, dict(opt_field=[0, 1, 2], shopt_surf_inds=[list(range(len(pr["patches"])))] * 3)
     pr = problems.cylinder(n_el=n_el, n_circ=n_circ, n_axial=n_axial, R=1.0, L=2.0 * n_axial, E=68e9, nu=0.35, h_th=1e-2,
                            pressure_like_load=(0.0, 0.0, -1.0e3), quad_deg_const=3, thickness_kind="const")
     kw = dict(opt_field=[0, 1, 2], shopt_surf_inds=[list(range(n_circ * n_axial))] * 3)
@@ -382,7 +393,7 @@ def run_reference(args, rank):
     trend = []
     if not args.no_trend:
         for ne in (24, 48, 96):
-            if ne >= args.n_el:
+            if ne >= args.n_el or args.topology.lower() == "wingbox":
                 continue
             prs, kws = workload(ne, *topo(args))
             dts, inf = cpu_reference_iteration(prs, kws)
@@ -565,8 +576,11 @@ def main():
             # bounded CPU sample: ONE FULL iteration of the restated reference CPU path on a smaller mesh of the
             # same topology (value at THAT size, nothing scaled), with this GPU path timed on the same mesh
             # beside it; the full-size CPU number is `bench.py --impl reference`.
-            ne = min(args.cpu_n_el, args.n_el)
-            prs, kws = workload(ne, *topo(args))
+            if args.topology.lower() == "wingbox":
+                ne, sample_topo = 0, ("wingbox", min(1.2e5, float(args.dofs)))
+            else:
+                ne, sample_topo = min(args.cpu_n_el, args.n_el), topo(args)
+            prs, kws = workload(ne, *sample_topo)
             tm = {}
             dt, inf = cpu_reference_iteration(prs, kws, tm)
             dms = DeviceModel(prs, **kws)
@@ -583,11 +597,11 @@ def main():
             gpu_s = a.elapsed_time(b) / 3e3
             line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "iters/s", "cores": cpu_threads(), "kind": "port",
                                     "sample": "one FULL analysis+adjoint iteration of the restated CPU path (C++/OpenMP assembly incl. penalty, "
-                                              "multifrontal LU per Newton step + re-factorised adjoint, %d threads) on cylinder_%s_ne%d "
+                                              "multifrontal LU per Newton step + re-factorised adjoint, %d threads) on %s "
                                               "(N=%d, %.1f s, %d Newton its); NOT scaled to the headline size -- the same mesh on this GPU "
                                               "path takes %.4f s (same_config_gpu_value)"
-                                              % (cpu_threads(), args.topology, ne, inf["dofs"], dt, inf["newton_its"], gpu_s),
-                                    "sample_config": {"workload": workload_name(ne, *topo(args)), "dofs": inf["dofs"]},
+                                              % (cpu_threads(), workload_name(ne, *sample_topo).split(":")[0], inf["dofs"], dt, inf["newton_its"], gpu_s),
+                                    "sample_config": {"workload": workload_name(ne, *sample_topo), "dofs": inf["dofs"]},
                                     "cpu_phase_s": {k: round(v, 3) for k, v in tm.items()},
                                     "same_config_gpu_value": 1.0 / gpu_s, "same_config_gpu_krylov_its": sts.info["krylov_its"],
                                     "W_int_cpu": inf["W_int"], "W_int_gpu": float(dms.wv_sum[0].item())}

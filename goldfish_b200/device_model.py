@@ -49,13 +49,16 @@ def _nccl_comm(lib, dist, device):
 class DeviceCsr:
     """CSR matrix whose arrays live in HBM."""
 
-    def __init__(self, nrows, ncols, indptr, indices, device):
+    def __init__(self, nrows, ncols, indptr, indices, device, share=None):
         self.nrows, self.ncols = int(nrows), int(ncols)
         self.indptr_h = np.ascontiguousarray(indptr, dtype=np.int64)
         self.indices_h = np.ascontiguousarray(indices, dtype=np.int32)
         self.nnz = int(self.indptr_h[-1])
-        self.indptr = torch.from_numpy(self.indptr_h).to(device)
-        self.indices = torch.from_numpy(self.indices_h).to(device)
+        if share is not None:             # same pattern as another matrix: one copy of the index arrays in HBM
+            self.indptr, self.indices = share.indptr, share.indices
+        else:
+            self.indptr = torch.from_numpy(self.indptr_h).to(device)
+            self.indices = torch.from_numpy(self.indices_h).to(device)
         self.vals = torch.zeros(max(self.nnz, 1), dtype=torch.float64, device=device)
         self._t = None
         self.device = device
@@ -159,7 +162,10 @@ class DeviceModel:
         self.theta = up(S.theta0, np.float64)
         # operators
         self.K = DeviceCsr(S.N, S.N, S.K_indptr, S.K_indices, dv)
-        self.P = [DeviceCsr(S.N, S.P_ncols[i], S.P_indptr[i], S.P_indices[i], dv) for i in range(len(S.opt_field))]
+        self.P = []
+        for i in range(len(S.opt_field)):
+            twin = next((self.P[j] for j in range(i) if S.P_indices[j] is S.P_indices[i]), None)
+            self.P.append(DeviceCsr(S.N, S.P_ncols[i], S.P_indptr[i], S.P_indices[i], dv, share=twin))
         self.T = DeviceCsr(S.N, S.n_th, S.T_indptr, S.T_indices, dv)
         self.penP = []
         # outputs
@@ -576,9 +582,11 @@ class DeviceModel:
             self._dist_c = d
         return self._dist_c
 
-    def _gmres(self, b, x, rtol, max_it, restart=30):
+    def _gmres(self, b, x, rtol, max_it, restart=None):
         """Right-preconditioned GMRES(restart) with the current preconditioner (fallback of _krylov)."""
         n = self.sym.N
+        if restart is None:            # indefinite systems stagnate under short restarts: as long as ~4 GB of basis allow
+            restart = int(max(20, min(100, n, 4e9 / (16.0 * n))))
         if getattr(self, "_gm", None) is None or self._gm[2] != restart:
             dv = self.device
             t = dict(V=torch.empty((restart + 1) * n, dtype=torch.float64, device=dv),

@@ -218,8 +218,14 @@ def wingbox(h=0.05, n_seg=10, n_spar=3, n_rib=17, L=10.0, C=2.0, H=0.4, p=3, E=6
     so no two meshes match.  Root (x = 0) clamped with two CP layers, dead pressure on the upper skin.
     target_dofs: choose h so that the model has about that many displacement dofs."""
     if target_dofs is not None:
-        area = 2 * L * C + n_spar * L * H + n_rib * 0.8 * C * H
-        h = float(np.sqrt(3.0 * area / target_dofs)) * 1.04
+        dims = [(L / n_seg, C)] * (2 * n_seg) + [(L, H)] * n_spar + [(0.8 * C if n_spar > 1 else C, H)] * n_rib
+
+        def count(hh):
+            return sum(3 * (max(4, int(np.ceil(a / (hh * (1 + 0.04 * (s % 6)))))) + p) * (max(4, int(np.ceil(b / (hh * (1 + 0.04 * (s % 6)))))) + p)
+                       for s, (a, b) in enumerate(dims))
+        h = float(np.sqrt(3.0 * sum(a * b for a, b in dims) / target_dofs))
+        for _ in range(6):
+            h *= float(np.sqrt(count(h) / target_dofs))
     xs = np.linspace(0.0, L, n_seg + 1)
     y_sp = np.linspace(0.1 * C, 0.9 * C, n_spar) if n_spar > 1 else np.array([0.5 * C])
     ya, yb = float(y_sp[0]), float(y_sp[-1])

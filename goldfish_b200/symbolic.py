@@ -286,7 +286,12 @@ class Symbolic:
     # --------------------------------------------------------------- P patterns
     def _P_patterns(self):
         self.P_indptr, self.P_indices = [], []
+        cache = {}
         for fi, field in enumerate(self.opt_field):
+            key = tuple(self.shopt_surf_inds[fi])
+            if key in cache:              # same patch list => same pattern and column offsets: share the arrays
+                self.P_indptr.append(cache[key][0]); self.P_indices.append(cache[key][1])
+                continue
             rowlen = np.zeros(self.N, dtype=np.int64)
             for s in self.shopt_surf_inds[fi]:
                 P = self.patches[s]
@@ -303,6 +308,7 @@ class Symbolic:
                     base = indptr[P.dof_off + i * P.ncp + a_idx]
                     indices[base + loc[a_idx, m_idx]] = P.pcol_off[field] + cand[a_idx, m_idx]
             self.P_indptr.append(indptr); self.P_indices.append(indices)
+            cache[key] = (indptr, indices)
 
     # ---------------------------------------------------------------- T pattern
     def _T_pattern(self):

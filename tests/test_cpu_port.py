@@ -11,7 +11,7 @@ from oracle.cpu_port import CpuModel
 from goldfish_b200 import _capi as capi
 
 
-@pytest.mark.parametrize("case", ["tbeam_small", "slr_small"])
+@pytest.mark.parametrize("case", ["tbeam_small", "slr_small", "wingbox_small"])
 def test_port_matches_numpy_oracle(case):
     pr, kw = getattr(cases, case)()
     cm = CpuModel(pr, **kw)
@@ -51,6 +51,23 @@ def test_port_iteration_matches_numpy_oracle():
     for i, f in enumerate(kw["opt_field"]):
         gp = om.dWdCP(f, kw["shopt_surf_inds"][i]) - om.dRdCP(f, kw["shopt_surf_inds"][i]).T @ lam
         assert np.linalg.norm(grads[i] - gp) < 1e-8 * np.linalg.norm(gp)
+
+
+def test_wingbox_total_gradient_against_finite_differences():
+    """The reference's own check (check_totals) on the wing-box topology, through the CPU port: adjoint total
+    derivative of W_int w.r.t. one patch thickness against a central difference of converged Newton solves."""
+    pr, kw = cases.wingbox_small()
+    cm = CpuModel(pr, **kw)
+    th0 = cm.theta.copy()
+    _, g = cm.iteration(newton_rtol=1e-10)
+    ip, h = 3, 1e-4 * th0[3]
+
+    def W_at(d):
+        cm.theta[:] = th0; cm.theta[ip] += d
+        cm.iteration(newton_rtol=1e-10)
+        return cm.W
+    fd = (W_at(h) - W_at(-h)) / (2 * h)
+    assert abs(fd - g[-1][ip]) < 1e-6 * abs(fd)
 
 
 def test_multifrontal_lu_matches_superlu():

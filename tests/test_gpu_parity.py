@@ -33,7 +33,7 @@ def _assembled(DM, pr, kw, u):
     return dm
 
 
-@pytest.mark.parametrize("case", ["tbeam_small", "slr_small"])
+@pytest.mark.parametrize("case", ["tbeam_small", "slr_small", "wingbox_small"])
 def test_operators_match_live_oracle(DM, case):
     pr, kw = getattr(cases, case)()
     om = OracleModel(pr)
