@@ -151,7 +151,7 @@ __global__ void k_penalty_gather_P(GfPenalty Q, GfPenaltyP PP) {
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int64_t pos = PP.pos[n * 3 + i];
-    if (pos >= 0) PP.vals[pos] = s[i];
+    if (pos >= 0) PP.vals[pos] += s[i];     // rounds of interfaces accumulate; the caller zeroes vals first
   }
 }
 

@@ -250,6 +250,10 @@ class DeviceModel:
         self.true_rtol = float(_os.environ.get("GF_TRUE_RTOL", "1e-8"))
         self.pass_rtol = float(_os.environ.get("GF_PASS_RTOL", "1e-6"))       # recurrence tolerance of the first pass
         self.max_refine = 3
+        # small systems (latency-bound, an extra pass costs well under a millisecond) always get a second
+        # residual-replacement pass: the reference's own fixtures are the worst conditioned ones (C1 plate: kappa ~ 1.5e12,
+        # where a 1e-8 true residual leaves 3e-8 in the adjoint vector)
+        self.polish = S.N < 200000
         self.gmres_fallback = True
         self.fallback_used = False
         self.last_true_relres = None
@@ -279,6 +283,7 @@ class DeviceModel:
         self.pen_t = {}
         q = capi.GfPenalty()
         q.n_eval = pen["n_eval"]
+        self._penP_cache = {}
         pen = self._shard["pen"]          # destinations restricted to owned rows (all of them on 1 GPU)
         if pen["n_eval"] > 0:
             for k in ("connA", "connB", "connC0", "connC1", "basA", "basB", "basC0", "basC1", "tpar", "alpha",
@@ -295,19 +300,26 @@ class DeviceModel:
                 if pp_all.get("n_dest", 0) == 0:
                     self.penP.append(None)           # no penalty part at all (the same on every rank)
                     continue
-                M = DeviceCsr(S.N, S.P_ncols[S.opt_field.index(pp["field"])], pp["indptr"], pp["indices"], self.device)
-                if pp.get("n_dest", 0) == 0:
-                    # this rank owns none of the destinations: keep an all-zero part so that every rank
-                    # holds the same number of parts (one all-reduce per part in DeviceMat products)
-                    self.penP.append((M, None))
-                    continue
-                s = capi.GfPenaltyP()
-                s.n_dest = pp["n_dest"]
-                arrs = [up(pp[k] if len(pp[k]) else np.zeros(1, pp[k].dtype)) for k in ("ptr", "item_eval", "item_code", "pos")]
-                s.ptr, s.item_eval, s.item_code, s.pos = [_ptr(a) for a in arrs]
-                s.vals = _ptr(M.vals)
-                s.field = pp["field"]
-                self.penP.append((M, s))
+                twin = next((q[0] for q, qa in zip(self.penP, S.penP) if q is not None and qa["indices"] is pp_all["indices"]), None)
+                M = DeviceCsr(S.N, S.P_ncols[S.opt_field.index(pp["field"])], pp["indptr"], pp["indices"], self.device, share=twin)
+                # one gather struct per ROUND of interfaces with disjoint destinations (rounds accumulate); a rank that
+                # owns none of the destinations keeps the all-zero part, so that every rank holds the same number of
+                # parts (one all-reduce per part in DeviceMat products)
+                structs = []
+                for rd in pp["rounds"]:
+                    if rd["n_dest"] == 0:
+                        continue
+                    s = capi.GfPenaltyP()
+                    s.n_dest = rd["n_dest"]
+                    key = id(rd["item_eval"])
+                    if key not in self._penP_cache:       # the same gather lists serve the three fields
+                        self._penP_cache[key] = [up(rd[k] if len(rd[k]) else np.zeros(1, rd[k].dtype)) for k in ("ptr", "item_eval", "item_code", "pos")]
+                    arrs = self._penP_cache[key]
+                    s.ptr, s.item_eval, s.item_code, s.pos = [_ptr(a) for a in arrs]
+                    s.vals = _ptr(M.vals)
+                    s.field = pp["field"]
+                    structs.append(s)
+                self.penP.append((M, structs))
         else:
             self.penP = [None for _ in S.opt_field]
         self.pen_struct = q
@@ -422,8 +434,8 @@ class DeviceModel:
                 for pp in self.penP:
                     if pp is not None:
                         pp[0].vals.zero_()
-                        if pp[1] is not None:
-                            capi.check(lib.gf_penalty_gather_P(C.byref(self.pen_struct), C.byref(pp[1]), st), "gather_P")
+                        for rd in pp[1]:
+                            capi.check(lib.gf_penalty_gather_P(C.byref(self.pen_struct), C.byref(rd), st), "gather_P")
         if residual:
             self.allreduce(self.R)
             capi.check(lib.gf_mask_vec(C.byref(self.model), _ptr(self.R), st), "gf_mask_vec")
@@ -714,9 +726,9 @@ class DeviceModel:
             self.spmv_global(self.K, x, self._w_res, alpha=-1.0, beta=1.0)
             tr = (self.dot(self._w_res, self._w_res) ** 0.5 / bn) if bn > 0 else 0.0
             self.last_true_relres = tr
-            if tr <= self.true_rtol or k == self.max_refine:
+            if k == self.max_refine or (tr <= self.true_rtol and not (self.polish and k < 2)):
                 break
-            its2, rel2 = self._krylov(self._w_res, self._w_cor, min(1e-1, max(0.3 * self.true_rtol / tr, 1e-9)), max_it)
+            its2, rel2 = self._krylov(self._w_res, self._w_cor, min(1e-2 if tr <= self.true_rtol else 1e-1, max(0.3 * self.true_rtol / tr, 1e-9)), max_it)
             self.last_krylov_its += its2
             self.last_relres = rel2 * tr
             self.axpby(1.0, self._w_cor, 1.0, x)

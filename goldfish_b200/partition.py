@@ -65,13 +65,25 @@ def shard_symbolic(S, owner, rank):
         pen["K_pos"] = np.ascontiguousarray(pen["K_pos"][kK]); pen["nK"] = int(kK.sum())
     out["pen"] = pen
     penP = []
+    done = {}                    # the fields of one patch list share their gather lists: filter them once
     for pp in getattr(S, "penP", []):
         pp = dict(pp)
-        if pp["n_dest"] > 0:
-            kP = own[pp["dest_patch"]]
-            ptr2, ev2 = filter_ragged(pp["ptr"], pp["item_eval"], kP)
-            _, code2 = filter_ragged(pp["ptr"], pp["item_code"], kP)
-            pp.update(ptr=ptr2, item_eval=ev2, item_code=code2, pos=np.ascontiguousarray(pp["pos"][kP]), n_dest=int(kP.sum()))
+        rid = id(pp.get("rounds"))
+        if rid in done:
+            pp["rounds"], pp["n_dest_own"] = done[rid]
+            penP.append(pp)
+            continue
+        rounds = []
+        for rd in pp.get("rounds", []):
+            rd = dict(rd)
+            kP = own[rd["dest_patch"]]
+            ptr2, ev2 = filter_ragged(rd["ptr"], rd["item_eval"], kP)
+            _, code2 = filter_ragged(rd["ptr"], rd["item_code"], kP)
+            rd.update(ptr=ptr2, item_eval=ev2, item_code=code2, pos=np.ascontiguousarray(rd["pos"][kP]), n_dest=int(kP.sum()))
+            rounds.append(rd)
+        pp["rounds"] = rounds
+        pp["n_dest_own"] = int(sum(rd["n_dest"] for rd in rounds))
+        done[rid] = (rounds, pp["n_dest_own"])
         penP.append(pp)
     out["penP"] = penP
     return out

@@ -80,13 +80,29 @@ class SchwarzSetup:
                     return e, np.maximum(h, 1e-300)
                 eu, hu = direction(1, 0); ev, hv = direction(0, 1)
                 off = Xall[extra] - Xall[own][nn]
-                ou = (off * eu).sum(1) / hu; ov = (off * ev).sum(1) / hv
-                s_e, f_e = (In + ou, Jn + ov) if swap else (Jn + ov, In + ou)
+                pu = (off * eu).sum(1); pv = (off * ev).sum(1)
+                ou = pu / hu; ov = pv / hv
+                # overlap nodes of a patch that stands ON this one (T-/X-junction: rib on skin) lie out of the own
+                # surface: fold their normal distance into the slow key, so that the sheet is laid down along the
+                # slow direction instead of piling all its layers into one row (which would widen the band)
+                on = np.sqrt(np.maximum((off * off).sum(1) - pu * pu - pv * pv, 0.0)) / (hu if swap else hv)
+                on = np.where(on > 0.25, on, 0.0) * float(__import__("os").environ.get("GF_SW_FOLD", "1"))
+                s_e, f_e = (In + ou + on, Jn + ov) if swap else (Jn + ov + on, In + ou)
                 ks = np.concatenate([ks, s_e]); kf = np.concatenate([kf, f_e])
             nodes = np.concatenate([own, extra])
             order = np.lexsort((kf, ks))
-            nodes = nodes[order]
-            self.blocks.append(self._finish_block(nodes, G, n_s, dof, ncp, cpo, n_own=len(own)))
+            best = self._finish_block(nodes[order], G, n_s, dof, ncp, cpo, n_own=len(own))
+            if len(extra) and best["mb"] > 10:
+                # wide band: overlap nodes that do not continue the own grid (sheets standing on it, several
+                # interfaces meeting).  Try a reverse Cuthill-McKee ordering of the block's own graph and keep the
+                # ordering with the smaller band storage.
+                from scipy.sparse.csgraph import reverse_cuthill_mckee
+                sub = G[nodes][:, nodes]
+                rcm = np.asarray(reverse_cuthill_mckee(sub.astype(np.int32), symmetric_mode=True), dtype=np.int64)
+                alt = self._finish_block(nodes[rcm], G, n_s, dof, ncp, cpo, n_own=len(own))
+                if int(alt["mbj"].sum()) < int(best["mbj"].sum()):
+                    best = alt
+            self.blocks.append(best)
             self.blocks[-1]["patch"] = P.index
 
     def keep_blocks(self, mask):

@@ -362,6 +362,7 @@ class Symbolic:
         ev_lists = {k: [] for k in ("connA", "connB", "connC0", "connC1", "basA", "basB", "basC0", "basC1",
                                     "tpar", "alpha", "dofA", "dofB")}
         self.itf_alpha = []
+        self.itf_eval_range = []; n_acc = 0
         override = self.problem.get("alpha_override")
         for ii, T in enumerate(self.itf):
             PA, PB = self.patches[T["sA"]], self.patches[T["sB"]]
@@ -375,6 +376,7 @@ class Symbolic:
                 ad, ar = override[ii]
             self.itf_alpha.append((ad, ar))
             n = len(v)
+            self.itf_eval_range.append((n_acc, n_acc + n)); n_acc += n
             ev_lists["connA"].append(PA.cp_off + T["connA"][v]); ev_lists["connB"].append(PB.cp_off + T["connB"][v])
             ev_lists["connC0"].append(PA.cp_off + T["connA"][c]); ev_lists["connC1"].append(PA.cp_off + T["connA"][c + 1])
             ev_lists["basA"].append(T["DA"][v][:, 0:3, :]); ev_lists["basB"].append(T["DB"][v][:, 0:3, :])
@@ -440,38 +442,64 @@ class Symbolic:
             self.penP.append(pp)
 
     def _penalty_P(self, field, nodes):
+        """Gather lists of the penalty part of dR/dCP_f.  Built interface by interface (the item lists hold
+        32 x 6 x 16 entries per evaluation: one interface at a time keeps the temporaries small on coupling-heavy
+        models), then grouped into ROUNDS of interfaces whose destination sets are disjoint: inside a round every
+        destination has one owner thread, rounds run one after the other and accumulate (+=) -- deterministic."""
         pen = self.pen
-        n_eval = pen["n_eval"]
+        n_s = self.n_scalar
         dof = np.array([P.dof_off for P in self.patches]); ncp = np.array([P.ncp for P in self.patches])
         cpo = np.array([P.cp_off for P in self.patches])
         pcol = np.array([P.pcol_off[field] for P in self.patches])
-        # column blocks: (conn array, xblock id)
-        blocks = [(pen["connC0"], 0), (pen["connC1"], 1), (pen["connA"], 2), (pen["connA"], 3),
-                  (pen["connB"], 4), (pen["connB"], 5)]
-        rs, cs, evs, codes = [], [], [], []
-        la = np.arange(32)
-        for conn, xb in blocks:
-            conn = conn.astype(np.int64)
-            r = np.repeat(nodes, 16, axis=1)                    # [n_eval, 32*16]
-            c = np.tile(conn, (1, 32))
-            code = (np.repeat(la, 16) | (xb << 5) | (np.tile(np.arange(16), 32) << 8))[None, :].repeat(n_eval, 0)
-            ev = np.repeat(np.arange(n_eval, dtype=np.int64)[:, None], 512, axis=1)
-            keep = pcol[self.scalar_patch[c]] >= 0
-            rs.append(r[keep]); cs.append(c[keep]); evs.append(ev[keep]); codes.append(code[keep])
-        r = np.concatenate(rs); c = np.concatenate(cs); ev = np.concatenate(evs); code = np.concatenate(codes)
+        names = ("connC0", "connC1", "connA", "connA", "connB", "connB")          # xblock 0..5
+        la16 = np.repeat(np.arange(32, dtype=np.int32), 16); lb32 = np.tile(np.arange(16, dtype=np.int32), 32)
+        per_itf = []
+        for ii, (e0, e1) in enumerate(self.itf_eval_range):
+            ne = e1 - e0
+            rs, cs, evs, codes = [], [], [], []
+            nd = nodes[e0:e1]
+            for xb, nm in enumerate(names):
+                conn = pen[nm][e0:e1].astype(np.int64)
+                r = np.repeat(nd, 16, axis=1)                     # [ne, 512]
+                c = np.tile(conn, (1, 32))
+                keep = pcol[self.scalar_patch[c]] >= 0
+                if not keep.any():
+                    continue
+                code = np.broadcast_to((la16 | (xb << 5) | (lb32 << 8))[None, :], (ne, 512))
+                ev = np.broadcast_to(np.arange(e0, e1, dtype=np.int32)[:, None], (ne, 512))
+                rs.append(r[keep]); cs.append(c[keep]); evs.append(ev[keep]); codes.append(code[keep])
+            if not rs:
+                per_itf.append(None)
+                continue
+            r = np.concatenate(rs); c = np.concatenate(cs); ev = np.concatenate(evs); code = np.concatenate(codes)
+            key = r * n_s + c
+            order = np.argsort(key, kind="stable")
+            uk, start = np.unique(key[order], return_index=True)
+            per_itf.append(dict(uk=uk, ptr=np.append(start, len(key)).astype(np.int64),
+                                item_eval=ev[order].astype(np.int32), item_code=code[order].astype(np.int32)))
         out = dict(field=field)
-        if len(r) == 0:
-            out.update(n_dest=0)
+        live = [i for i, d in enumerate(per_itf) if d is not None]
+        if not live:
+            out.update(n_dest=0, rounds=[])
             return out
-        key = r * self.n_scalar + c
-        order = np.argsort(key, kind="stable")
-        uk, start = np.unique(key[order], return_index=True)
-        ur, uc = uk // self.n_scalar, uk % self.n_scalar
-        out["ptr"] = np.append(start, len(key)).astype(np.int64)
-        out["item_eval"] = ev[order].astype(np.int32); out["item_code"] = code[order].astype(np.int32)
-        out["n_dest"] = len(uk)
-        out["dest_patch"] = self.scalar_patch[ur].astype(np.int32)
-        # CSR of the penalty part: rows = dofs, cols = pcol + local cp
+        # rounds: greedy colouring of the "destination sets intersect" graph (only interfaces sharing a patch can)
+        color = {}
+        for i in live:
+            pi = set((self.itf[i]["sA"], self.itf[i]["sB"]))
+            used = set()
+            for j in live:
+                if j >= i:
+                    break
+                if pi & set((self.itf[j]["sA"], self.itf[j]["sB"])) and color[j] not in used:
+                    if np.intersect1d(per_itf[i]["uk"], per_itf[j]["uk"], assume_unique=True).size:
+                        used.add(color[j])
+            k = 0
+            while k in used:
+                k += 1
+            color[i] = k
+        # CSR of the penalty part over ALL destinations: rows = dofs, cols = pcol + local cp
+        uk_all = np.unique(np.concatenate([per_itf[i]["uk"] for i in live]))
+        ur, uc = uk_all // n_s, uk_all % n_s
         pr, pc = self.scalar_patch[ur], self.scalar_patch[uc]
         col = pcol[pc] + (uc - cpo[pc])
         rows = np.stack([dof[pr] + i * ncp[pr] + (ur - cpo[pr]) for i in range(3)], axis=1)     # [n,3]
@@ -480,11 +508,26 @@ class Symbolic:
         indptr = np.zeros(self.N + 1, dtype=np.int64)
         np.cumsum(np.bincount(rr, minlength=self.N), out=indptr[1:])
         out["indptr"] = indptr; out["indices"] = cc[o2].astype(np.int32)
-        pos = np.empty(len(rr), dtype=np.int64); pos[o2] = np.arange(len(rr))
-        pos = pos.reshape(-1, 3)
-        pos = np.where(self.bc_mask[rows] != 0, -1, pos)     # apply_row_bcs, diag = 0
-        out["pos"] = np.ascontiguousarray(pos)
+        pos_all = np.empty(len(rr), dtype=np.int64); pos_all[o2] = np.arange(len(rr))
+        pos_all = pos_all.reshape(-1, 3)
+        pos_all = np.where(self.bc_mask[rows] != 0, -1, pos_all)     # apply_row_bcs, diag = 0
         out["nnz"] = len(rr)
+        out["n_dest"] = len(uk_all)
+        rounds = []
+        for k in range(max(color.values()) + 1):
+            members = [i for i in live if color[i] == k]
+            ptrs, evs, codes, uks, off = [], [], [], [], 0
+            for i in members:
+                d = per_itf[i]
+                ptrs.append(d["ptr"][:-1] + off); off += int(d["ptr"][-1])
+                evs.append(d["item_eval"]); codes.append(d["item_code"]); uks.append(d["uk"])
+            uk = np.concatenate(uks)
+            idx = np.searchsorted(uk_all, uk)
+            rounds.append(dict(ptr=np.append(np.concatenate(ptrs), off).astype(np.int64),
+                               item_eval=np.concatenate(evs), item_code=np.concatenate(codes),
+                               pos=np.ascontiguousarray(pos_all[idx]), n_dest=len(uk),
+                               dest_patch=self.scalar_patch[uk // n_s].astype(np.int32)))
+        out["rounds"] = rounds
         return out
 
     # -------------------------------------------------------------- const loads

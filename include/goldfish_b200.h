@@ -154,7 +154,9 @@ int gf_penalty_gather_K(const GfModel* m, const GfPenalty* p, void* stream);
 
 /* Penalty part of dR/dCP_f, kept as its own small CSR (its pattern reaches
  * one element beyond the shell stencil through the chord-length term).
- * One thread per destination (row node, column CP): 3 values (row fields).
+ * One thread per destination (row node, column CP): 3 values (row fields), ACCUMULATED into vals: the host
+ * groups the intersections into rounds with disjoint destination sets and calls this once per round
+ * (fixed order => deterministic); the caller zeroes vals before the first round.
  * item code: la (5 bits: side*16 + a) | xblock << 5 (3 bits) | lb << 8 (4 bits);
  * xblock: 0 X_A(c), 1 X_A(c+1), 2 X_A,1, 3 X_A,2, 4 X_B,1, 5 X_B,2. */
 typedef struct GfPenaltyP {

@@ -348,7 +348,7 @@ extern "C" int gfo_penalty_gather_P(const GfPenalty* p, const GfPenaltyP* pp) {
       const double* H = Q.HuX + ev * 324 + (sa * 9) * 18 + xb * 3 + PP.field;
       for (int k = 0; k < 3; ++k) { const double w = bR[k * 16 + a] * cC; for (int i = 0; i < 3; ++i) s[i] += w * H[(3 * k + i) * 18]; }
     }
-    for (int i = 0; i < 3; ++i) { const int64_t pos = PP.pos[n * 3 + i]; if (pos >= 0) PP.vals[pos] = s[i]; }
+    for (int i = 0; i < 3; ++i) { const int64_t pos = PP.pos[n * 3 + i]; if (pos >= 0) PP.vals[pos] += s[i]; }
   }
   return 0;
 }

@@ -137,13 +137,16 @@ class CpuModel:
                 if pp.get("n_dest", 0) == 0:
                     continue
                 vals = np.zeros(pp["nnz"])
-                s = capi.GfPenaltyP()
-                s.n_dest = pp["n_dest"]
-                arrs = [np.ascontiguousarray(pp[k]) for k in ("ptr", "item_eval", "item_code", "pos")]
-                s.ptr, s.item_eval, s.item_code, s.pos = [_p(a) for a in arrs]
-                s.vals, s.field = _p(vals), pp["field"]
+                structs, keep = [], []
+                for rd in pp["rounds"]:
+                    s = capi.GfPenaltyP()
+                    s.n_dest = rd["n_dest"]
+                    arrs = [np.ascontiguousarray(rd[k]) for k in ("ptr", "item_eval", "item_code", "pos")]
+                    s.ptr, s.item_eval, s.item_code, s.pos = [_p(a) for a in arrs]
+                    s.vals, s.field = _p(vals), pp["field"]
+                    structs.append(s); keep.append(arrs)
                 M = sp.csr_matrix((vals, pp["indices"], pp["indptr"]), shape=(S.N, S.P_ncols[i]))
-                self.penP[i] = (M, s, arrs, vals)
+                self.penP[i] = (M, structs, keep, vals)
         self.pen = q
 
     def set_u(self, u):
@@ -176,7 +179,8 @@ class CpuModel:
                 for pp in self.penP:
                     if pp is not None:
                         pp[3][:] = 0
-                        self.lib.gfo_penalty_gather_P(C.byref(self.pen), C.byref(pp[1]))
+                        for rd in pp[1]:
+                            self.lib.gfo_penalty_gather_P(C.byref(self.pen), C.byref(rd))
         if what & capi.GF_OUT_R:
             self.R[S.bc_list] = 0.0
         if what & capi.GF_OUT_K:

@@ -24,7 +24,7 @@ def _worker(rank, world, port, q):
     mine = dict(elems=np.sort(sh["color_elem"]).tolist(),
                 nR=sh["pen"]["nR"], nK=sh["pen"]["nK"], items_K=int(len(sh["pen"]["K_item"])),
                 rows=sh["own_ranges"].tolist(), owner=owner.tolist(),
-                nP=[pp.get("n_dest", 0) for pp in sh["penP"]])
+                nP=[pp.get("n_dest_own", 0) for pp in sh["penP"]])
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
     # colour lists stay conflict free and sorted by colour
@@ -37,7 +37,7 @@ def _worker(rank, world, port, q):
               and sum(g["nK"] for g in gathered) == S.pen["nK"]
               and sum(g["items_K"] for g in gathered) == len(S.pen["K_item"])
               and all(g["owner"] == gathered[0]["owner"] for g in gathered)
-              and [sum(g["nP"][i] for g in gathered) for i in range(len(S.penP))] == [pp["n_dest"] for pp in S.penP])
+              and [sum(g["nP"][i] for g in gathered) for i in range(len(S.penP))] == [sum(rd["n_dest"] for rd in pp["rounds"]) for pp in S.penP])
         covered = np.zeros(S.N, dtype=int)
         for g in gathered:
             for b0, b1 in g["rows"]:

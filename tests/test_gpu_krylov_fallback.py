@@ -37,8 +37,10 @@ def test_indefinite_tangent_falls_back_to_gmres(built_lib):
     x = dm.solve(b, refactor=True).cpu().numpy()
     assert dm.fallback_used and dm.precond_is_reference
     xe = spla.splu(K.tocsc()).solve(b.cpu().numpy())
-    assert np.linalg.norm(x - xe) < 1e-8 * np.linalg.norm(xe)
+    # an indefinite system: the residual is what GMRES controls (and what the LU answer itself is good to)
     assert dm.last_true_relres < 1e-8
+    assert np.linalg.norm(K @ x - b.cpu().numpy()) < 1e-8 * np.linalg.norm(b.cpu().numpy())
+    assert np.linalg.norm(x - xe) < 1e-5 * np.linalg.norm(xe)
 
 
 def test_gmres_matches_pcg_on_spd_system(built_lib):
