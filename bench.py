@@ -204,7 +204,7 @@ def e2e_step(nm, ops, cp_host, th_host):
     return W, V, grads, u
 
 
-def build_facade(pr, kw, symbolic=None):
+def build_facade(pr, kw, symbolic=None, device_model=None):
     from goldfish_b200.nonmatching_opt import NonMatchingOpt, SplinePatch, Thickness, ShellLoad
     from goldfish_b200.operations import DispImOpeartion, IntEnergyExOperation, VolumeExOperation
     splines = [SplinePatch(P["knots"], P["p"], P["cp"], P["quad_deg"], P["bc_dofs"]) for P in pr["patches"]]
@@ -216,6 +216,7 @@ def build_facade(pr, kw, symbolic=None):
                            pr["penalty_coefficient"], 1)
     nm.set_residuals([ShellLoad(body_force=P["body_force"]) for P in pr["patches"]])
     nm._symbolic = symbolic          # same topology as the device-resident arm: reuse its symbolic phase
+    nm._device_model = device_model  # ... and (large runs) its whole device model
     return nm, (DispImOpeartion(nm), IntEnergyExOperation(nm), VolumeExOperation(nm))
 
 
@@ -475,7 +476,7 @@ def main():
     value = args.steps / (ms * 1e-3)              # one patch-sharded problem over all ranks (strong scaling)
 
     # ---- e2e through the facade, host arrays ----
-    nm, ops = build_facade(pr, kw, symbolic=S)
+    nm, ops = build_facade(pr, kw, symbolic=S, device_model=dm)
     cp_host = {f: np.concatenate([cp[P.cp_off:P.cp_off + P.ncp, f] for P in S.patches]) for f in kw["opt_field"]}
     for _ in range(max(1, args.warmup - 1)):
         e2e_step(nm, ops, cp_host, th)

@@ -24,14 +24,34 @@ def _coarse_knots(kn, p, nc):
     return coarse, missing
 
 
-def build(problem, nc=8):
-    """Returns (coarse_problem, P) with P the (N x Nc) scipy CSR prolongation."""
+def coarsening_ratio(problem, target_dofs, r_min=7.0):
+    """Uniform coarsening ratio r (fine elements per coarse element and direction, >= r_min) for which the coarse
+    model has about target_dofs dofs: every patch is coarsened isotropically, so long thin patches (spars, ribs)
+    keep their aspect ratio instead of getting a fixed number of coarse elements per side."""
+    ne = [(len(np.unique(pd["knots"][0])) - 1, len(np.unique(pd["knots"][1])) - 1) for pd in problem["patches"]]
+    p = problem["patches"][0]["p"][0]
+
+    def dofs(r):
+        return sum(3 * (max(2, int(np.ceil(a / r))) + p) * (max(2, int(np.ceil(b / r))) + p) for a, b in ne)
+    r = float(r_min)
+    while dofs(r) > target_dofs and r < 1e4:
+        r *= 1.05
+    return r
+
+
+def build(problem, nc=8, ratio=None):
+    """Returns (coarse_problem, P) with P the (N x Nc) scipy CSR prolongation.  nc: coarse elements per side of
+    every patch; ratio (overrides nc): fine elements per coarse element, per direction and patch."""
     patches_c, blocks = [], []
     for pd in problem["patches"]:
         p = pd["p"][0]
         ku, kv = [np.asarray(k, dtype=np.float64) for k in pd["knots"]]
         n_u, n_v = bsp.num_basis(ku, p), bsp.num_basis(kv, p)
-        cu, mu = _coarse_knots(ku, p, nc); cv, mv = _coarse_knots(kv, p, nc)
+        if ratio is not None:
+            ncu = max(2, int(np.ceil((len(np.unique(ku)) - 1) / ratio))); ncv = max(2, int(np.ceil((len(np.unique(kv)) - 1) / ratio)))
+        else:
+            ncu = ncv = nc
+        cu, mu = _coarse_knots(ku, p, ncu); cv, mv = _coarse_knots(kv, p, ncv)
         Pu, ku2 = bsp.knot_insertion_operator(cu, p, mu); Pv, kv2 = bsp.knot_insertion_operator(cv, p, mv)
         assert np.allclose(ku2, ku) and np.allclose(kv2, kv)
         X = np.asarray(pd["cp"], dtype=np.float64).reshape(n_v, n_u, 4)

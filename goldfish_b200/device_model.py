@@ -98,10 +98,6 @@ class DeviceModel:
             raise capi.GoldfishError("goldfish_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = capi.load()
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
-        self.sym = symbolic if symbolic is not None else Symbolic(problem, opt_field, shopt_surf_inds)
-        S = self.sym
-        dv = self.device
-        self._keep = []
         # ---- patch-sharded multi-GPU mode (one process per GPU, torch.distributed / NCCL) ----
         import torch.distributed as tdist
         if distributed is None:
@@ -110,7 +106,16 @@ class DeviceModel:
         self.rank = tdist.get_rank() if distributed else 0
         self.world = tdist.get_world_size() if distributed else 1
         from .partition import lpt_partition, shard_symbolic
-        self.owner = lpt_partition([P.nel for P in S.patches], self.world)
+        nel = [(len(np.unique(P["knots"][0])) - 1) * (len(np.unique(P["knots"][1])) - 1) for P in problem["patches"]]
+        self.owner = lpt_partition(nel, self.world)
+        if symbolic is not None:
+            self.sym = symbolic
+        else:
+            self.sym = Symbolic(problem, opt_field, shopt_surf_inds,
+                                own_patches=(self.owner == self.rank) if distributed else None)
+        S = self.sym
+        dv = self.device
+        self._keep = []
         self.own_patches = [P.index for P in S.patches if self.owner[P.index] == self.rank]
         self._shard = shard_symbolic(S, self.owner, self.rank)
         self.own_ranges = self._shard["own_ranges"]
@@ -211,7 +216,7 @@ class DeviceModel:
             if self.world > 1:
                 for cand in ((24, 96), (24, 48), (24, 24), (12, 24)):
                     self.schwarz_sub = cand
-                    if _SS.count_subdomains(S.patches, cand) >= 148 * self.world:
+                    if _SS.count_subdomains(S.patches, cand) >= 2 * 148 * self.world:      # two resident CTAs per SM
                         break
         import os as _os0
         if _os0.environ.get("GF_SW_SUB"):                  # tuning experiments: "48" or "24,96"
@@ -220,16 +225,18 @@ class DeviceModel:
         if _os0.environ.get("GF_SW_LAYERS"):
             self.schwarz_layers = int(_os0.environ["GF_SW_LAYERS"])
         max_ne = max(max(P.neu, P.nev) for P in S.patches)
+        self.coarse_ratio = None
         if coarse_nc == "auto":
-            # the coarse sweeps run beside the fine ones: keep their chain shorter than the fine chains
-            # (which shrink per GPU when the blocks are spread over several ranks)
-            # (thread-block-cluster coarse sweeps: ~1.8 us per block step measured on B200)
-            coarse_nc = 0 if max_ne < 16 else int(min(28, max(8, max_ne // 7)))
-            if self.world > 1:
-                # sharded: the coarse solve is a dense product with a row slab of Kc^-1 (no chain to keep short), so
-                # the level does not shrink with the GPU count; bound the dense inverse to ~48 k coarse dofs
-                while coarse_nc > 8 and 3 * len(S.patches) * (coarse_nc + 3) ** 2 > 48000:
-                    coarse_nc -= 1
+            # Coarse spline level: every patch coarsened by one ratio r >= 7 in both directions, r grown until the level
+            # has <= 24 k dofs on one GPU (its sweeps are one latency chain on a thread-block cluster that must hide
+            # behind the fine sweeps: 23 k dofs = 720 block steps = 1.4 ms at C3) or <= 48 k in sharded runs (there the
+            # coarse solve is a dense product with a row slab of Kc^-1, so the level does not shrink with the GPU count).
+            if max_ne < 16:
+                coarse_nc = 0
+            else:
+                from . import coarse as coarse_mod
+                self.coarse_ratio = coarse_mod.coarsening_ratio(problem, 24000 if self.world < 2 else 48000)
+                coarse_nc = max(2, int(np.ceil(max_ne / self.coarse_ratio)))
         self.coarse_nc = int(coarse_nc) if precond == "schwarz" else 0
         self.problem = problem
         self._pc = None
@@ -297,11 +304,12 @@ class DeviceModel:
             q.g, q.Huu, q.HuX = _ptr(self.pen_g), _ptr(self.pen_Huu), _ptr(self.pen_HuX)
             q.nR, q.nK = pen["nR"], pen["nK"]
             for pp, pp_all in zip(self._shard["penP"], S.penP):
-                if pp_all.get("n_dest", 0) == 0:
-                    self.penP.append(None)           # no penalty part at all (the same on every rank)
-                    continue
-                twin = next((q[0] for q, qa in zip(self.penP, S.penP) if q is not None and qa["indices"] is pp_all["indices"]), None)
-                M = DeviceCsr(S.N, S.P_ncols[S.opt_field.index(pp["field"])], pp["indptr"], pp["indices"], self.device, share=twin)
+                # the part exists on EVERY rank as soon as the model has intersections (possibly with an empty pattern
+                # on a rank that owns none of its destinations): DeviceMat products issue one all-reduce per part
+                ip = pp.get("indptr", np.zeros(S.N + 1, dtype=np.int64)); ix = pp.get("indices", np.zeros(0, dtype=np.int32))
+                twin = next((q[0] for q, qa in zip(self.penP, S.penP) if q is not None and qa.get("indices") is not None
+                             and qa.get("indices") is pp_all.get("indices")), None)
+                M = DeviceCsr(S.N, S.P_ncols[S.opt_field.index(pp["field"])], ip, ix, self.device, share=twin)
                 # one gather struct per ROUND of interfaces with disjoint destinations (rounds accumulate); a rank that
                 # owns none of the destinations keeps the all-zero part, so that every rank holds the same number of
                 # parts (one all-reduce per part in DeviceMat products)
@@ -523,7 +531,7 @@ class DeviceModel:
             self._coarse = None
             if self.coarse_nc > 0:
                 from . import coarse as coarse_mod
-                cpr, P = coarse_mod.build(self.problem, nc=self.coarse_nc)
+                cpr, P = coarse_mod.build(self.problem, nc=self.coarse_nc, ratio=self.coarse_ratio)
                 cpr["alpha_override"] = self.sym.itf_alpha
                 cm = DeviceModel(cpr, device=self.device, precond="schwarz", coarse_nc=0, distributed=False)
                 cm._single_block = True
@@ -721,6 +729,9 @@ class DeviceModel:
         bn = self.dot(b, b) ** 0.5
         its, rel = self._krylov(b, x, self.pass_rtol, max_it)
         self.last_krylov_its, self.last_relres = its, rel
+        if not bn > 0.0:                  # zero right-hand side: x = 0 exactly
+            self.last_true_relres = 0.0
+            return x
         for k in range(self.max_refine + 1):
             self._w_res.copy_(b)
             self.spmv_global(self.K, x, self._w_res, alpha=-1.0, beta=1.0)
@@ -728,7 +739,7 @@ class DeviceModel:
             self.last_true_relres = tr
             if k == self.max_refine or (tr <= self.true_rtol and not (self.polish and k < 2)):
                 break
-            its2, rel2 = self._krylov(self._w_res, self._w_cor, min(1e-2 if tr <= self.true_rtol else 1e-1, max(0.3 * self.true_rtol / tr, 1e-9)), max_it)
+            its2, rel2 = self._krylov(self._w_res, self._w_cor, min(1e-2 if tr <= self.true_rtol else 1e-1, max(0.3 * self.true_rtol / max(tr, 1e-300), 1e-9)), max_it)
             self.last_krylov_its += its2
             self.last_relres = rel2 * tr
             self.axpby(1.0, self._w_cor, 1.0, x)
@@ -781,6 +792,7 @@ class DeviceModel:
             if (it > 0 and rel < rtol) or ref == 0.0:
                 break
             if it == max_it:
+                self.newton_history, self.newton_krylov_its, self.newton_true_relres = hist, kits, trel
                 raise capi.GoldfishNotConverged("Nonlinear solver failed to converge in %d iterations" % max_it)
             self.axpby(-1.0, self.R, 0.0, rhs)
             self.solve(rhs, du, refactor=(it == 0))

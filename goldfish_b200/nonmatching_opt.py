@@ -192,8 +192,10 @@ class NonMatchingOpt:
         if self._dm is None:
             self.problem = self._problem()
             # a caller that already ran the symbolic phase for this topology may hand it over (`_symbolic`)
-            self._dm = DeviceModel(self.problem, self.opt_field, self.shopt_surf_inds, device=self.device,
-                                   symbolic=getattr(self, "_symbolic", None))
+            # ... or the whole device model of the same problem (`_device_model`: bench.py times the device-resident
+            # step and the facade step on ONE model instead of building the set-up twice)
+            self._dm = getattr(self, "_device_model", None) or DeviceModel(
+                self.problem, self.opt_field, self.shopt_surf_inds, device=self.device, symbolic=getattr(self, "_symbolic", None))
             S = self._dm.sym
             dv = self._dm.device
             self.vec_iga_nest = DeviceVec.zeros(self.vec_iga_dof_list, dv, self._dm)

@@ -35,8 +35,12 @@ class PatchSym:
 
 
 class Symbolic:
-    def __init__(self, problem, opt_field=(), shopt_surf_inds=(), build_transpose=True):
+    def __init__(self, problem, opt_field=(), shopt_surf_inds=(), build_transpose=True, own_patches=None):
+        """own_patches: optional boolean array over the patches (patch-sharded runs): the coupling gather lists
+        are then built only for destinations whose ROW belongs to an own patch -- the only ones that rank uses --
+        which divides the host time and memory of the coupling set-up by about the number of ranks."""
         self.problem = problem
+        self.own_patches = None if own_patches is None else np.asarray(own_patches, dtype=bool)
         self.opt_field = list(opt_field)
         self.shopt_surf_inds = [list(x) for x in shopt_surf_inds]
         self.alpha = float(problem.get("penalty_coefficient", 1.0e3))
@@ -402,6 +406,9 @@ class Symbolic:
         nodes = np.concatenate([pen["connA"], pen["connB"]], axis=1).astype(np.int64)   # [n_eval, 32]
         item = (np.arange(n_eval, dtype=np.int64)[:, None] * 32 + np.arange(32)[None, :]).ravel()
         dest = nodes.ravel()
+        if self.own_patches is not None:                 # sharded: destinations in own patches only
+            keep = self.own_patches[self.scalar_patch[dest]]
+            item, dest = item[keep], dest[keep]
         order = np.argsort(dest, kind="stable")
         ud, start = np.unique(dest[order], return_index=True)
         pen["R_ptr"] = np.append(start, len(dest)).astype(np.int64)
@@ -411,9 +418,17 @@ class Symbolic:
         pen["nR"] = len(ud)
         pen["R_dest_patch"] = ps.astype(np.int32)
         # ---- K gather: destination = (row CP, col CP) ----
-        r = np.repeat(nodes, 32, axis=1).ravel(); c = np.tile(nodes, (1, 32)).ravel()
+        ev_ids = np.arange(n_eval, dtype=np.int64)
+        nd = nodes
+        if self.own_patches is not None:                 # sharded: evaluations that touch an own patch ...
+            touch = self.own_patches[self.scalar_patch[nodes[:, 0]]] | self.own_patches[self.scalar_patch[nodes[:, 16]]]
+            ev_ids, nd = ev_ids[touch], nodes[touch]
+        r = np.repeat(nd, 32, axis=1).ravel(); c = np.tile(nd, (1, 32)).ravel()
         la = np.repeat(np.arange(32), 32); lb = np.tile(np.arange(32), 32)
-        item = (np.arange(n_eval, dtype=np.int64)[:, None] * 1024 + (la * 32 + lb)[None, :]).ravel()
+        item = (ev_ids[:, None] * 1024 + (la * 32 + lb)[None, :]).ravel()
+        if self.own_patches is not None:                 # ... and of those the destinations whose row is owned
+            keep = self.own_patches[self.scalar_patch[r]]
+            r, c, item = r[keep], c[keep], item[keep]
         key = r * self.n_scalar + c
         order = np.argsort(key, kind="stable")
         uk, start = np.unique(key[order], return_index=True)
@@ -458,11 +473,16 @@ class Symbolic:
             ne = e1 - e0
             rs, cs, evs, codes = [], [], [], []
             nd = nodes[e0:e1]
+            if self.own_patches is not None and not (self.own_patches[self.itf[ii]["sA"]] or self.own_patches[self.itf[ii]["sB"]]):
+                per_itf.append(None)                     # sharded: neither side is an own patch
+                continue
             for xb, nm in enumerate(names):
                 conn = pen[nm][e0:e1].astype(np.int64)
                 r = np.repeat(nd, 16, axis=1)                     # [ne, 512]
                 c = np.tile(conn, (1, 32))
                 keep = pcol[self.scalar_patch[c]] >= 0
+                if self.own_patches is not None:
+                    keep &= self.own_patches[self.scalar_patch[r]]
                 if not keep.any():
                     continue
                 code = np.broadcast_to((la16 | (xb << 5) | (lb32 << 8))[None, :], (ne, 512))

@@ -83,9 +83,12 @@ def test_baseline_configs_match_goldens(DM, case, gold):
     u = dm.newton(max_it=30, rtol=1e-3).cpu().numpy()
     assert len(dm.newton_history) == len(g["newton_hist"])
     assert np.linalg.norm(u - g["u_newton"]) < TOL_SOL * np.linalg.norm(g["u_newton"])
-    # objective + adjoint total derivative dW/dt at the Newton state
-    dm.assemble(tangent=True, functionals=True, thickness=True)
     assert abs(float(dm.wv_sum[0]) - g["W_newton"]) < TOL_SOL * abs(g["W_newton"])
+    # objective + adjoint total derivative dW/dt AT THE GOLDEN'S Newton state: the adjoint vector is K(u)^-1 dW/du(u), and
+    # with kappa ~ 1e12 a 5e-9 difference in u (allowed above) moves it by several 1e-8; evaluated at the same u the
+    # comparison measures the linear solve itself
+    dm.set_u(g["u_newton"])
+    dm.assemble(tangent=True, functionals=True, thickness=True)
     rhs = dm.dWdu.clone()
     rhs[torch.from_numpy(dm.sym.bc_list.astype(np.int64)).cuda()] = 0.0
     lam = dm.solve(rhs)

@@ -41,7 +41,7 @@ def test_sweep_kernels_agree(built_lib, sub):
     for mode in ("single_nocluster", "single"):
         zs, xs, i_s = out[mode]
         assert np.isfinite(zs).all() and rel(zs, zg) < 1e-3      # FP32 panel products, different summation order
-        assert abs(ig - i_s) <= 5                                # convergence is checked every 5 iterations
+        assert abs(ig - i_s) <= 15                               # two passes, each checked every 5 iterations
         assert rel(xs, xg) < 1e-8
     xe = spla.splu(dm.K.to_scipy().tocsc()).solve(b.cpu().numpy())
     assert rel(xs, xe) < 1e-6
