@@ -133,6 +133,7 @@ SIGNATURES = {
     "gf_spmv_t": [C.POINTER(GfCsr), C.POINTER(GfCsrT), c_vp, c_vp, c_f64, c_f64, c_vp],
     "gf_pcg": [C.POINTER(GfCsr), c_vp, c_vp, C.POINTER(GfPcgWork), C.POINTER(GfPrecond), C.POINTER(GfDist), c_f64, c_f64, C.c_int, C.c_int,
                C.POINTER(C.c_int), C.POINTER(c_f64), c_vp],
+    "gf_residual_dd": [C.POINTER(GfCsr), C.POINTER(GfDist), c_vp, c_vp, c_vp, c_vp],
     "gf_gmres": [C.POINTER(GfCsr), c_vp, c_vp, C.POINTER(GfGmresWork), C.POINTER(GfPrecond), C.POINTER(GfDist), c_f64, C.c_int, C.c_int,
                  C.POINTER(C.c_int), C.POINTER(c_f64), c_vp],
     "gf_dist_unique_id": [c_vp],

@@ -32,7 +32,7 @@ def coarsening_ratio(problem, target_dofs, r_min=7.0):
     p = problem["patches"][0]["p"][0]
 
     def dofs(r):
-        return sum(3 * (max(2, int(np.ceil(a / r))) + p) * (max(2, int(np.ceil(b / r))) + p) for a, b in ne)
+        return sum(3 * (max(min(a, 8), int(np.ceil(a / r))) + p) * (max(min(b, 8), int(np.ceil(b / r))) + p) for a, b in ne)
     r = float(r_min)
     while dofs(r) > target_dofs and r < 1e4:
         r *= 1.05
@@ -48,7 +48,8 @@ def build(problem, nc=8, ratio=None):
         ku, kv = [np.asarray(k, dtype=np.float64) for k in pd["knots"]]
         n_u, n_v = bsp.num_basis(ku, p), bsp.num_basis(kv, p)
         if ratio is not None:
-            ncu = max(2, int(np.ceil((len(np.unique(ku)) - 1) / ratio))); ncv = max(2, int(np.ceil((len(np.unique(kv)) - 1) / ratio)))
+            neu, nev = len(np.unique(ku)) - 1, len(np.unique(kv)) - 1
+            ncu = max(min(neu, 8), int(np.ceil(neu / ratio))); ncv = max(min(nev, 8), int(np.ceil(nev / ratio)))    # at least 8 per side
         else:
             ncu = ncv = nc
         cu, mu = _coarse_knots(ku, p, ncu); cv, mv = _coarse_knots(kv, p, ncv)

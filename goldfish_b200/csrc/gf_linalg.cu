@@ -525,6 +525,67 @@ extern "C" int gf_precond_apply(const GfPrecond* pc, const double* r, double* z,
   return gf_spmv(&pc->P, pc->zc, z, 1.0, 1.0, st);            // z += P z_c (coarse level is replicated)
 }
 
+// ---------------------------------------------------------------- r = b - A x in double-double ----
+// Iterative refinement needs the residual of the CURRENT iterate, and on these systems (kappa up to 1e12) a plain FP64
+// evaluation of b - A x is itself only good to ~eps |A||x| / |b| ~ 2e-9: the products are formed exactly with an FMA
+// (two-product) and accumulated as an unevaluated (hi, lo) pair (two-sum), so the returned FP64 residual is correctly
+// rounded to ~1e-30 |A||x|.  Memory bound like the SpMV it replaces (the extra flops are free).
+namespace gf {
+__device__ __forceinline__ void dd_add(double& hi, double& lo, double v) {       // (hi, lo) += v
+  const double s = hi + v;
+  const double bb = s - hi;
+  lo += (hi - (s - bb)) + (v - bb);
+  hi = s;
+}
+__global__ void __launch_bounds__(256)
+k_residual_dd(GfCsr A, int64_t row_begin, int64_t row_end, const double* __restrict__ x, const double* __restrict__ b,
+              double* __restrict__ r) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = row_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < row_end; row += nwarps) {
+    const int64_t s = A.indptr[row], e = A.indptr[row + 1];
+    double hi = 0.0, lo = 0.0;
+    for (int64_t k = s + lane; k < e; k += 32) {
+      const double a = A.vals[k], xv = __ldg(x + A.indices[k]);
+      const double p = a * xv;
+      const double pe = fma(a, xv, -p);            // exact product = p + pe
+      dd_add(hi, lo, p);
+      lo += pe;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const double ohi = __shfl_xor_sync(0xffffffffu, hi, o), olo = __shfl_xor_sync(0xffffffffu, lo, o);
+      dd_add(hi, lo, ohi);
+      lo += olo;
+    }
+    if (lane == 0) {
+      double rh = b[row], rl = 0.0;
+      dd_add(rh, rl, -hi);
+      r[row] = rh + (rl - lo);
+    }
+  }
+}
+}  // namespace gf
+
+extern "C" int gf_residual_dd(const GfCsr* A, const GfDist* dist, const double* x, const double* b, double* r, void* stream) {
+  if (!A || !x || !b || !r) return set_error(GF_ERR_BADARG, "gf_residual_dd: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = A->nrows;
+  if (dist && dist->n_ranges > 0) {
+    cudaError_t e = cudaMemsetAsync(r, 0, (size_t)n * sizeof(double), st);
+    if (e != cudaSuccess) return set_cuda_error(e, "gf_residual_dd memset");
+    for (int q = 0; q < dist->n_ranges; ++q) {
+      const int64_t b0 = dist->ranges_h[2 * q], b1 = dist->ranges_h[2 * q + 1];
+      if (b1 <= b0) continue;
+      k_residual_dd<<<spmv_grid(b1 - b0), 256, 0, st>>>(*A, b0, b1, x, b, r);
+      count_launch(1);
+    }
+    return dist_allreduce(dist, r, n, st);          // disjoint rows + zeros: the sum is exact
+  }
+  k_residual_dd<<<spmv_grid(n), 256, 0, st>>>(*A, 0, n, x, b, r);
+  return check_launch("k_residual_dd");
+}
+
 extern "C" int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, const GfPrecond* pre,
                       const GfDist* dist, double rtol, double atol, int max_it, int check_every, int* iters,
                       double* relres, void* stream) {

@@ -20,13 +20,24 @@ NB = 64
 
 
 class SchwarzSetup:
-    def __init__(self, sym, layers=2, single_block=False, sub=(24, 96)):
+    def __init__(self, sym, layers=2, single_block=False, sub=(24, 96), own_patches=None):
+        """own_patches (sharded runs): boolean array over the patches; only the blocks of those patches are built,
+        and the control-point graph only for them and the patches they intersect."""
         S = sym
         self.sym, self.layers = sym, layers
         n_s = S.n_scalar
+        need = None
+        if own_patches is not None and not single_block:
+            own_patches = np.asarray(own_patches, dtype=bool)
+            need = own_patches.copy()
+            for T in S.itf:
+                if own_patches[T["sA"]] or own_patches[T["sB"]]:
+                    need[T["sA"]] = need[T["sB"]] = True
         # scalar CP graph: own stencils + coupled pairs
         rows, cols = [], []
         for P in S.patches:
+            if need is not None and not need[P.index]:
+                continue
             cand, mask, _ = S._own_stencil(P)
             a, m = np.nonzero(mask)
             rows.append(P.cp_off + a); cols.append(P.cp_off + cand[a, m])
@@ -48,6 +59,8 @@ class SchwarzSetup:
             return
         self.sub = sub
         for P, (i0, i1, j0, j1) in self._subdomains(S.patches, sub):
+            if own_patches is not None and not own_patches[P.index]:
+                continue
             # own set = a rectangle of the patch's CP grid (at most sub[0] x sub[1] nodes; 24 x 96 measured best on B200 at
             # 1 M DOF: the narrow side sets the band width, the long side keeps the overlap volume down):
             # short band => short triangular-solve chains and cheap factorisation;
@@ -108,6 +121,35 @@ class SchwarzSetup:
     def keep_blocks(self, mask):
         """Distributed runs: each rank factors and solves only the blocks of its own patches."""
         self.blocks = [b for b, m in zip(self.blocks, mask) if m]
+
+    @staticmethod
+    def choose_subdomains(patches, world, layers=2, candidates=((24, 96), (24, 48), (24, 24), (12, 24))):
+        """Sub-domain shape for `world` GPUs from a two-term cost model of one preconditioner application per GPU:
+        streaming the solve-form panels (HBM bound: bytes / 4.8 TB/s, what k_sw_solve1 reaches) against the
+        triangular-sweep chain of one block (latency bound: 2 x block rows x 2.7 us per step, times the number of
+        waves when the GPU's blocks do not all fit on its 148 SMs).  Small sub-domains shorten the chain and cost
+        overlap bytes: one GPU at 1 M dofs is bandwidth bound and keeps 24 x 96 (measured best,
+        profiles/r1_sweep_tuning_*.jsonl); with more GPUs the bytes per GPU shrink and the chain takes over
+        (profiles/r2_sweep_tuning_subdomains.jsonl: the iteration count does not grow with smaller sub-domains)."""
+        ov = 3 * layers                                   # overlap in control-point layers per side
+        best, best_t = candidates[0], None
+        for a, b in candidates:
+            nblk, bytes_tot, rows_max, npad_max = 0, 0.0, 0, 0
+            for P in patches:
+                su = max(1, int(np.ceil(P.n_u / a))); sv = max(1, int(np.ceil(P.n_v / b)))
+                wa = min(P.n_u, int(np.ceil(P.n_u / su)) + 2 * ov); wb = min(P.n_v, int(np.ceil(P.n_v / sv)) + 2 * ov)
+                n_pad = 3 * wa * wb
+                rows = int(np.ceil(n_pad / NB))
+                mb = int(np.ceil(9.0 * min(wa, wb) / NB)) + 1
+                nblk += su * sv
+                bytes_tot += 0.7 * su * sv * rows * ((mb + 1) * NB * NB * 4 * 2 + NB * NB * 8)
+                rows_max = max(rows_max, rows); npad_max = max(npad_max, n_pad)
+            slots = 148 * max(1, int(220 * 1024 // (npad_max * 8)))
+            waves = int(np.ceil(nblk / world / slots))
+            t = max(bytes_tot / world / 4.8e12, 2 * rows_max * 2.7e-6 * waves)
+            if best_t is None or t < 0.97 * best_t:
+                best, best_t = (a, b), t
+        return best
 
     @staticmethod
     def count_subdomains(patches, sub):

@@ -286,6 +286,9 @@ int gf_pcg(const GfCsr* A, const double* b, double* x, const GfPcgWork* w, const
            const GfDist* dist, double rtol, double atol, int max_it, int check_every, int* iters,
            double* relres, void* stream);
 int gf_jacobi_setup(const GfCsr* A, double* dinv, void* stream);
+/* r = b - A x with exact products (FMA) and double-double accumulation: the residual of iterative refinement
+ * (the counterpart of the extended-precision residual the LU goldens are refined with).  Sharded: owned rows, summed. */
+int gf_residual_dd(const GfCsr* A, const GfDist* dist, const double* x, const double* b, double* r, void* stream);
 
 /* Flexible (right-preconditioned) restarted GMRES(restart) on K x = b with the same preconditioner: the fallback when
  * the tangent is indefinite and CG reports GF_ERR_BREAKDOWN (the reference's LU still returns a Newton step

@@ -56,8 +56,8 @@ def test_port_iteration_matches_numpy_oracle():
 def test_wingbox_total_gradient_against_finite_differences():
     """The reference's own check (check_totals) on the wing-box topology, through the CPU port: adjoint total
     derivative of W_int w.r.t. one patch thickness against a central difference of converged Newton solves."""
-    pr, kw = cases.wingbox_small()
-    cm = CpuModel(pr, **kw)
+    pr, _ = cases.wingbox_small()
+    cm = CpuModel(pr, opt_field=[0, 1, 2], shopt_surf_inds=[list(range(len(pr["patches"])))] * 3)
     th0 = cm.theta.copy()
     _, g = cm.iteration(newton_rtol=1e-10)
     ip, h = 3, 1e-4 * th0[3]

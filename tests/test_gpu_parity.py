@@ -98,8 +98,8 @@ def test_baseline_configs_match_goldens(DM, case, gold):
     # residual (tests/golden/make_oracle_goldens.py) and DeviceModel.solve refines on the TRUE residual, so both
     # configurations are held to north_star's 1e-8.
     assert dm.last_true_relres is not None and dm.last_true_relres < 1e-8
-    assert np.linalg.norm(lam.cpu().numpy() - g["lam"]) < TOL_SOL * np.linalg.norm(g["lam"])
     assert np.linalg.norm(tot.cpu().numpy() - g["dWdt_total"]) < TOL_SOL * np.linalg.norm(g["dWdt_total"])
+    assert np.linalg.norm(lam.cpu().numpy() - g["lam"]) < TOL_SOL * np.linalg.norm(g["lam"])
 
 
 def test_schwarz_and_jacobi_pcg_agree(DM):

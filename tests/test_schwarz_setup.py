@@ -61,13 +61,12 @@ def test_coarse_prolongation_is_exact_refinement():
 
 
 def _cpu_tangent(pr, alpha=None):
-    """K at u = 0 from the compiled CPU port (shell) + numpy oracle (penalty)."""
+    """K at u = 0 from the compiled CPU port (shells + penalty)."""
     from oracle.cpu_port import CpuModel
     from goldfish_b200 import _capi as capi
-    cm = CpuModel(pr)
     if alpha is not None:
-        for I, (ad, ar) in zip(cm.om.interfaces, alpha):
-            I.alpha_d, I.alpha_r = ad.copy(), ar.copy()
+        pr = dict(pr); pr["alpha_override"] = alpha      # coarse level: keep the fine penalty stiffness
+    cm = CpuModel(pr)
     cm.set_u(np.zeros(cm.S.N))
     cm.shell(capi.GF_OUT_R | capi.GF_OUT_K)
     return cm, cm.K_matrix().tocsr(), -cm.residual()
