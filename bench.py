@@ -243,17 +243,22 @@ def parity_checks(dm, step, torch, world):
     out["newton_history_tight"] = [float(h) for h in dm.newton_history]
     out["newton_stopped_at_fp64_floor"] = bool(dm.newton_stagnated)
     tr = step.info["true_relres"]
-    out["true_relres_state"] = max(tr[:-1]) if len(tr) > 1 else None
+    # the first two Newton solves are the ones the timed (rtol 1e-3) iteration does; later ones act on a residual that
+    # already sits at its FP64 floor
+    out["true_relres_state"] = max(tr[:min(2, len(tr) - 1)]) if len(tr) > 1 else None
+    out["true_relres_state_all_tight_solves"] = tr[:-1]
     out["true_relres_adjoint"] = tr[-1]
     out["recurrence_rtol"] = dm.krylov_rtol
     W0 = float(dm.wv_sum[0].item())
     gT = step.gT.clone(); gP = [g.clone() for g in step.gP]
-    # symmetry of K: |K x - K^T x| / |K x| for a random x (rows owned by this rank; summed over ranks inside spmv_global)
+    # symmetry of K without forming K^T: |x.(K y) - y.(K x)| / (|x| |K y|) for two random vectors
     g = torch.Generator(device="cpu"); g.manual_seed(3)
     x = torch.randn(S.N, dtype=torch.float64, generator=g).to(dm.device)
-    y1 = torch.zeros_like(x); y2 = torch.zeros_like(x)
-    dm.spmv_global(dm.K, x, y1); dm.spmv_global(dm.K, x, y2, transpose=True)
-    out["K_asymmetry"] = float(torch.linalg.vector_norm(y1 - y2) / torch.linalg.vector_norm(y1))
+    y = torch.randn(S.N, dtype=torch.float64, generator=g).to(dm.device)
+    Kx = torch.zeros_like(x); Ky = torch.zeros_like(x)
+    dm.spmv_global(dm.K, x, Kx); dm.spmv_global(dm.K, y, Ky)
+    out["K_asymmetry"] = abs(dm.dot(x, Ky) - dm.dot(y, Kx)) / (dm.dot(x, x) ** 0.5 * dm.dot(Ky, Ky) ** 0.5)
+    del x, y, Kx, Ky
 
     def W_at(theta=None, cp=None):
         th0, cp0 = dm.theta.clone(), dm.cp.clone()
@@ -450,8 +455,17 @@ def main():
     from goldfish_b200 import _capi as capi
     from goldfish_b200.device_model import DeviceModel
     lib = capi.load()
+    t_setup = time.perf_counter()
+    setup = {}
+
+    def log(msg):
+        setup[msg] = round(time.perf_counter() - t_setup, 1)
+        if rank == 0:
+            print("[bench %7.1fs] %s" % (time.perf_counter() - t_setup, msg), file=sys.stderr, flush=True)
     pr, kw = workload(args.n_el, *topo(args))
+    log("problem built")
     dm = DeviceModel(pr, lean=problems_dofs(pr) > 4e6, **kw)
+    log("symbolic phase + upload")
     S = dm.sym
     cp, th = design_state(S)
     dm.cp.copy_(torch.from_numpy(cp)); dm.set_theta(th)
@@ -463,9 +477,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for i in range(args.warmup):
         step()
+        if i == 0:
+            torch.cuda.synchronize(); log("first step (incl. Schwarz + coarse set-up)")
     barrier()
+    log("warm-up done")
     l0 = lib.gf_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as cs:
@@ -477,6 +494,7 @@ def main():
         barrier()
     launches = lib.gf_launch_count() - l0
     ms = e0.elapsed_time(e1)
+    log("timed steps done")
     if world > 1:
         t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     value = args.steps / (ms * 1e-3)              # one patch-sharded problem over all ranks (strong scaling)
@@ -535,6 +553,7 @@ def main():
             phases[timers[i][0]] = phases.get(timers[i][0], 0.0) + timers[i - 1][1].elapsed_time(timers[i][1]) / len(step_timers)
     phases = {k: round(v, 2) for k, v in phases.items()}
     fac_ms = time_kernel(torch, lambda: dm.factor_preconditioner(), 2, flush)
+    log("kernel timings done")
     parity = None
     if not args.no_parity:
         try:
@@ -578,7 +597,7 @@ def main():
                                   "achieved_on_bytes_moved": ((8 + 4.0 / 3.0) * dm.K.nnz + 24 * S.N) / (spmv_ms * 1e-3) / 1e9,
                                   "launch_ms": spmv_ms,
                                   "rowwise_k_spmv_ms": spmv_row_ms, "rowwise_k_spmv_gbs": spmv_bytes / (spmv_row_ms * 1e-3) / 1e9},
-                "parity": parity,
+                "parity": parity, "setup_s": setup,
                 "kernels": kernels, "clocks": cs.summary()}
         if world == 1:
             line["other_configs"] = small_configs(torch)

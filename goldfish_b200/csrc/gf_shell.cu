@@ -490,7 +490,8 @@ struct WarpSmemK2 {
   int ninfo[16][8];
 };
 
-__global__ void __launch_bounds__(128)
+template <int OCC>      // resident CTAs per SM asked of the register allocator: 2 -> 255 registers, 3 -> 168 (experiment knob GF_SHELL_OCC)
+__global__ void __launch_bounds__(128, OCC)
 k_shell_k2(GfModel M, GfShellOut O, int what, int color_begin, int color_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -726,12 +727,15 @@ k_shell_k2(GfModel M, GfShellOut O, int what, int color_begin, int color_count) 
 
 static int launch_k2(const GfModel* m, int what, const GfShellOut* out, cudaStream_t st) {
   const size_t smem = 4 * sizeof(WarpSmemK2);
-  cudaError_t e = cudaFuncSetAttribute(k_shell_k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static const int occ = getenv("GF_SHELL_OCC") ? atoi(getenv("GF_SHELL_OCC")) : 2;
+  cudaError_t e = cudaFuncSetAttribute(k_shell_k2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_shell_k2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(k_shell_k2)");
   for (int c = 0; c < m->num_colors; ++c) {
     const int b = m->color_ptr_h[c], n = m->color_ptr_h[c + 1] - b;
     if (n <= 0) continue;
-    k_shell_k2<<<(n + 3) / 4, 128, smem, st>>>(*m, *out, what, b, n);
+    if (occ == 3) k_shell_k2<3><<<(n + 3) / 4, 128, smem, st>>>(*m, *out, what, b, n);
+    else k_shell_k2<2><<<(n + 3) / 4, 128, smem, st>>>(*m, *out, what, b, n);
     count_launch(1);
   }
   count_launch(-1);

@@ -267,9 +267,6 @@ class DeviceModel:
         # residual down to 1e-13: the reference's own fixtures are the worst conditioned ones (C1 plate: kappa ~ 1.5e12,
         # where a 1e-9 true residual still leaves 3e-8 in the adjoint vector)
         self.polish = S.N < 200000
-        self.polish_rtol = 1e-13
-        if self.polish:
-            self.max_refine = 5
         self.gmres_fallback = True
         self.fallback_used = False
         self.last_true_relres = None
@@ -752,7 +749,7 @@ class DeviceModel:
         if getattr(self, "_w_res", None) is None:
             self._w_res, self._w_cor = torch.empty_like(b), torch.empty_like(b)
         bn = self.dot(b, b) ** 0.5
-        its, rel = self._krylov(b, x, self.pass_rtol, max_it)
+        its, rel = self._krylov(b, x, 1e-11 if self.polish else self.pass_rtol, max_it)
         self.last_krylov_its, self.last_relres = its, rel
         if not bn > 0.0:                  # zero right-hand side: x = 0 exactly
             self.last_true_relres = 0.0
@@ -762,9 +759,15 @@ class DeviceModel:
                                                _ptr(self._w_res), self._stream()), "gf_residual_dd")
             tr = (self.dot(self._w_res, self._w_res) ** 0.5 / bn) if bn > 0 else 0.0
             self.last_true_relres = tr
-            if k == self.max_refine or tr <= (self.polish_rtol if self.polish else self.true_rtol):
+            if k == self.max_refine or (tr <= self.true_rtol and not (self.polish and k < 2)):
                 break
-            its2, rel2 = self._krylov(self._w_res, self._w_cor, min(1e-2 if tr <= self.true_rtol else 1e-1, max(0.3 * (self.polish_rtol if self.polish else self.true_rtol) / max(tr, 1e-300), 1e-4)), max_it)
+            if self.polish:
+                # a 2-norm residual says little about the soft modes that carry the error when kappa ~ 1e12: converge every
+                # correction far (1e-7 of ITS right-hand side, the exact residual of the current iterate)
+                cor_rtol = 1e-7
+            else:
+                cor_rtol = min(1e-1, max(0.3 * self.true_rtol / max(tr, 1e-300), 1e-4))
+            its2, rel2 = self._krylov(self._w_res, self._w_cor, cor_rtol, max_it)
             self.last_krylov_its += its2
             self.last_relres = rel2 * tr
             self.axpby(1.0, self._w_cor, 1.0, x)
