@@ -15,6 +15,7 @@
 #include <stdint.h>
 #include <string.h>
 #include <vector>
+#include <omp.h>
 #include "../../include/goldfish_b200.h"
 #include "../../goldfish_b200/csrc/kl_point.cuh"
 
@@ -361,3 +362,6 @@ extern "C" int gfo_bc_set_diag(const GfModel* m, double diag) {
   }
   return 0;
 }
+
+// torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm sets its thread count explicitly
+extern "C" void gfo_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }

@@ -355,6 +355,7 @@ int mf_solve(void* h, const double* b, double* x, const int64_t* perm) {
   return 0;
 }
 
+void mf_set_threads(void* h, int n) { if (n > 0) { omp_set_num_threads(n); ((Solver*)h)->nthreads = n; } }
 void mf_free_numeric(void* h) { free_numeric(*(Solver*)h); }
 void mf_destroy(void* h) { Solver* s = (Solver*)h; free_numeric(*s); delete s; }
 }

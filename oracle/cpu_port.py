@@ -44,6 +44,9 @@ class CpuModel:
         if not os.path.exists(LIB):
             build()
         self.lib = C.CDLL(LIB)
+        nthr = int(os.environ.get("GFO_THREADS", "0"))
+        if nthr > 0:
+            self.lib.gfo_set_threads(nthr)
         self.lib.gfo_shell_assemble.argtypes = [C.POINTER(capi.GfModel), C.c_int, C.POINTER(capi.GfShellOut)]
         self.problem = problem
         self.S = S = Symbolic(problem, opt_field, shopt_surf_inds)

@@ -83,6 +83,10 @@ class MultifrontalLU:
         st, self._dll = _openblas_set_threads()
         lib.mf_set_blas(self.h, _capsule_ptr(cb, "dgemm"), _capsule_ptr(cb, "dtrsm"), _capsule_ptr(cl, "dgetrf"),
                         _capsule_ptr(cl, "dlaswp"), _capsule_ptr(cb, "dgemv"), _capsule_ptr(cb, "dtrsv"), st, big)
+        nthr = int(os.environ.get("GFO_THREADS", "0"))
+        if nthr > 0:
+            lib.mf_set_threads.argtypes = [C.c_void_p, C.c_int]
+            lib.mf_set_threads(self.h, nthr)
         self.N, self.nfronts = N, nf
         self.flops = lib.mf_flops(self.h)
         self.lu_bytes = 8 * lib.mf_lu_doubles(self.h)
