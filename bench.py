@@ -138,6 +138,34 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class Watchdog:
+    """Guard for the optional, untimed sections that follow the measurement (parity checks, sharded-vs-single run,
+    extra configurations): if a section does not return within its allowance -- e.g. a collective some rank never
+    enters -- the bench line measured so far is printed with a note and every rank leaves with exit code 0, instead
+    of the whole run being killed at the driver's limit with nothing printed."""
+
+    def __init__(self, rank):
+        self.rank, self.line, self.timer = rank, None, None
+
+    def _fire(self, label, seconds):
+        try:
+            if self.rank == 0 and self.line is not None:
+                self.line.setdefault("notes", []).append("section '%s' did not finish within %d s; line printed by the watchdog" % (label, seconds))
+                sys.stdout.write(json.dumps(self.line) + "\n"); sys.stdout.flush()
+        finally:
+            os._exit(0)
+
+    def start(self, seconds, label):
+        self.cancel()
+        self.timer = threading.Timer(seconds, self._fire, args=(label, seconds))
+        self.timer.daemon = True
+        self.timer.start()
+
+    def cancel(self):
+        if self.timer is not None:
+            self.timer.cancel(); self.timer = None
+
+
 # ----------------------------------------------------------------------------- our arm
 SPMV_NODE_TRAFFIC_C3 = 1481301648   # dram read 1469338000 + write 11963648 B of one k_spmv_node launch at n_el = 201 (profiles/r2_ncu_full_k_spmv_node.csv)
 SWEEP_TRAFFIC_C3 = 7155089760      # dram read 7143036000 + write 12053760 B of one k_sw_solve1 launch at n_el = 201 (profiles/r2_ncu_full_k_sw_solve1.csv)
@@ -439,6 +467,42 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def cpu_baseline_sample(args, torch, DeviceModel):
+    """`cpu_baseline` of our arm's line (N = 1)."""
+    # bounded CPU sample: ONE FULL iteration of the restated reference CPU path on a smaller mesh of the
+    # same topology (value at THAT size, nothing scaled), with this GPU path timed on the same mesh
+    # beside it; the full-size CPU number is `bench.py --impl reference`.
+    if args.topology.lower() == "wingbox":
+        ne, sample_topo = 0, ("wingbox", min(1.2e5, float(args.dofs)))
+    else:
+        ne, sample_topo = min(args.cpu_n_el, args.n_el), topo(args)
+    prs, kws = workload(ne, *sample_topo)
+    tm = {}
+    dt, inf = cpu_reference_iteration(prs, kws, tm)
+    dms = DeviceModel(prs, **kws)
+    cps, ths = design_state(dms.sym)
+    dms.cp.copy_(torch.from_numpy(cps)); dms.set_theta(ths)
+    sts = Step(dms)
+    for _ in range(2):
+        sts()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        sts()
+    b.record(); torch.cuda.synchronize()
+    gpu_s = a.elapsed_time(b) / 3e3
+    return {"value": 1.0 / dt, "unit": "iters/s", "cores": cpu_threads(), "kind": "port",
+                            "sample": "one FULL analysis+adjoint iteration of the restated CPU path (C++/OpenMP assembly incl. penalty, "
+                                      "multifrontal LU per Newton step + re-factorised adjoint, %d threads) on %s "
+                                      "(N=%d, %.1f s, %d Newton its); NOT scaled to the headline size -- the same mesh on this GPU "
+                                      "path takes %.4f s (same_config_gpu_value)"
+                                      % (cpu_threads(), workload_name(ne, *sample_topo).split(":")[0], inf["dofs"], dt, inf["newton_its"], gpu_s),
+                            "sample_config": {"workload": workload_name(ne, *sample_topo), "dofs": inf["dofs"]},
+                            "cpu_phase_s": {k: round(v, 3) for k, v in tm.items()},
+                            "same_config_gpu_value": 1.0 / gpu_s, "same_config_gpu_krylov_its": sts.info["krylov_its"],
+                            "W_int_cpu": inf["W_int"], "W_int_gpu": float(dms.wv_sum[0].item())}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -563,22 +627,6 @@ def main():
                   "grad_thickness_norm": float(torch.linalg.vector_norm(step.gT).item()),
                   "grad_shape_norms": [float(torch.linalg.vector_norm(g).item()) for g in step.gP],
                   "true_relres": step.info.get("true_relres")}
-    parity = None
-    if not args.no_parity and (world == 1 or args.parity_sharded):
-        try:
-            parity = parity_checks(dm, step, torch, world)
-        except Exception as e:          # reported in the line, never hidden
-            parity = {"error": "%s: %s" % (type(e).__name__, e), "newton_history": [float(h) for h in getattr(dm, "newton_history", [])]}
-            step.newton_rtol = 1e-3
-        if world > 1:
-            parity["ranks_vs_single"] = ranks_vs_single(torch, dist, world, rank)
-    elif not args.no_parity:
-        # N > 1: the finite-difference / tight-Newton checks run on the N = 1 line (same workload); here the line
-        # carries the invariants above (W_int, |u|, |lambda|, gradient norms: equal to the N = 1 line's to solver
-        # tolerance) and the sharded-vs-single comparison is tests/test_gpu_parity.py::test_patch_sharded_two_gpus_match_single_gpu
-        # (`--parity-sharded` runs the full checks sharded as well)
-        parity = {"mode": "invariants only at N > 1 (see the N = 1 line for FD / true-residual checks)"}
-    log("parity done")
     kernels = {"phase_ms": phases, "precond_factor_ms": fac_ms, "spmv_ms": spmv_ms, "spmv_gbs": achieved, "sweeps_ms": sweep_ms, "sweeps_gbs": sweep_gbs,
                "assemble_RK_ms": asm_ms, "assemble_RK_material_tflops": asm_flops / (asm_ms * 1e-3) / 1e12,
                "assemble_RK_gbs_algorithmic": (8 * dm.K.nnz + 8 * (4 * S.n_scalar + S.N + S.n_th)) / (asm_ms * 1e-3) / 1e9,
@@ -613,46 +661,59 @@ def main():
                                   "achieved_on_bytes_moved": ((8 + 4.0 / 3.0) * dm.K.nnz + 24 * S.N) / (spmv_ms * 1e-3) / 1e9,
                                   "launch_ms": spmv_ms,
                                   "rowwise_k_spmv_ms": spmv_row_ms, "rowwise_k_spmv_gbs": spmv_bytes / (spmv_row_ms * 1e-3) / 1e9},
-                "parity": parity, "invariants": invariants, "setup_s": setup,
+                "parity": None, "invariants": invariants, "setup_s": setup,
                 "kernels": kernels, "clocks": cs.summary()}
+    else:
+        line = None
+    # ---------------- optional, untimed sections; each under the watchdog ----------------
+    wd = Watchdog(rank); wd.line = line
+    parity = None
+    if not args.no_parity:
+        if world == 1 or args.parity_sharded:
+            wd.start(300, "parity checks at the benched size")
+            try:
+                parity = parity_checks(dm, step, torch, world)
+            except Exception as e:          # reported in the line, never hidden
+                parity = {"error": "%s: %s" % (type(e).__name__, e), "newton_history": [float(h) for h in getattr(dm, "newton_history", [])]}
+                step.newton_rtol = 1e-3
+            wd.cancel()
+        else:
+            # N > 1: the finite-difference / tight-Newton checks run on the N = 1 line (same workload); this line carries
+            # the invariants (W_int, |u|, |lambda|, gradient norms: equal to the N = 1 line's to solver tolerance) and
+            # the sharded-vs-single comparison below (`--parity-sharded` runs the full checks sharded as well)
+            parity = {"mode": "N > 1: invariants + sharded-vs-single run; FD / tight-Newton checks are on the N = 1 line"}
+        if line is not None:
+            line["parity"] = parity
+        if world > 1:
+            wd.start(240, "sharded vs single-GPU run of a small model")
+            try:
+                rvs = ranks_vs_single(torch, dist, world, rank)
+            except Exception as e:
+                rvs = {"error": "%s: %s" % (type(e).__name__, e)}
+            wd.cancel()
+            parity["ranks_vs_single"] = rvs
+    log("parity done")
+    if rank == 0:
         if world == 1:
-            line["other_configs"] = small_configs(torch)
+            wd.start(120, "other configurations")
+            try:
+                line["other_configs"] = small_configs(torch)
+            except Exception as e:
+                line["other_configs"] = {"error": "%s: %s" % (type(e).__name__, e)}
+            wd.cancel()
         if not args.no_cpu_baseline and world == 1:     # reported at N = 1 only (bench contract)
-            # bounded CPU sample: ONE FULL iteration of the restated reference CPU path on a smaller mesh of the
-            # same topology (value at THAT size, nothing scaled), with this GPU path timed on the same mesh
-            # beside it; the full-size CPU number is `bench.py --impl reference`.
-            if args.topology.lower() == "wingbox":
-                ne, sample_topo = 0, ("wingbox", min(1.2e5, float(args.dofs)))
-            else:
-                ne, sample_topo = min(args.cpu_n_el, args.n_el), topo(args)
-            prs, kws = workload(ne, *sample_topo)
-            tm = {}
-            dt, inf = cpu_reference_iteration(prs, kws, tm)
-            dms = DeviceModel(prs, **kws)
-            cps, ths = design_state(dms.sym)
-            dms.cp.copy_(torch.from_numpy(cps)); dms.set_theta(ths)
-            sts = Step(dms)
-            for _ in range(2):
-                sts()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(3):
-                sts()
-            b.record(); torch.cuda.synchronize()
-            gpu_s = a.elapsed_time(b) / 3e3
-            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "iters/s", "cores": cpu_threads(), "kind": "port",
-                                    "sample": "one FULL analysis+adjoint iteration of the restated CPU path (C++/OpenMP assembly incl. penalty, "
-                                              "multifrontal LU per Newton step + re-factorised adjoint, %d threads) on %s "
-                                              "(N=%d, %.1f s, %d Newton its); NOT scaled to the headline size -- the same mesh on this GPU "
-                                              "path takes %.4f s (same_config_gpu_value)"
-                                              % (cpu_threads(), workload_name(ne, *sample_topo).split(":")[0], inf["dofs"], dt, inf["newton_its"], gpu_s),
-                                    "sample_config": {"workload": workload_name(ne, *sample_topo), "dofs": inf["dofs"]},
-                                    "cpu_phase_s": {k: round(v, 3) for k, v in tm.items()},
-                                    "same_config_gpu_value": 1.0 / gpu_s, "same_config_gpu_krylov_its": sts.info["krylov_its"],
-                                    "W_int_cpu": inf["W_int"], "W_int_gpu": float(dms.wv_sum[0].item())}
+            wd.start(300, "cpu_baseline sample")
+            try:
+                line["cpu_baseline"] = cpu_baseline_sample(args, torch, DeviceModel)
+            except Exception as e:
+                line["cpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, e)}
+            wd.cancel()
         print(json.dumps(line), flush=True)
+        wd.line = None                      # printed: the watchdog must not print it again
     if world > 1:
+        wd.start(60, "process-group shutdown")
         dist.destroy_process_group()
+        wd.cancel()
 
 
 if __name__ == "__main__":

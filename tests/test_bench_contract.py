@@ -37,3 +37,19 @@ def test_other_ranks_print_nothing():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, env=env, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_watchdog_prints_the_line_and_exits_zero():
+    """A post-measurement section that never returns (a collective some rank does not enter) must not cost the
+    measured line: the watchdog prints it with a note and leaves with exit code 0."""
+    code = ("import sys, time; sys.path.insert(0, %r); import bench\n"
+            "wd = bench.Watchdog(0); wd.line = {'metric': 'm', 'value': 1.0}\n"
+            "wd.start(1, 'hanging section'); time.sleep(30); print('not reached')\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "not reached" not in out.stdout
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["value"] == 1.0 and "hanging section" in line["notes"][0]
+    code2 = ("import sys, time; sys.path.insert(0, %r); import bench\n"
+             "wd = bench.Watchdog(1); wd.start(1, 'x'); wd.cancel(); time.sleep(2); print('finished')\n" % ROOT)
+    out2 = subprocess.run([sys.executable, "-c", code2], capture_output=True, text=True, timeout=60)
+    assert out2.returncode == 0 and out2.stdout.strip() == "finished"
