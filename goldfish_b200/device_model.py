@@ -118,6 +118,9 @@ class DeviceModel:
         self.world = tdist.get_world_size() if distributed else 1
         from .partition import lpt_partition, shard_symbolic
         nel = [(len(np.unique(P["knots"][0])) - 1) * (len(np.unique(P["knots"][1])) - 1) for P in problem["patches"]]
+        if self.world > len(nel):
+            raise ValueError("patch-sharded run with more ranks (%d) than spline patches (%d): every rank must own a patch"
+                             % (self.world, len(nel)))
         self.owner = lpt_partition(nel, self.world)
         if symbolic is not None:
             self.sym = symbolic
