@@ -11,6 +11,7 @@ intersections with their mortar parametric coordinates.
                    (BASELINE C1; geometry + intersection tables from tests/golden/plate_c1_input.npz)
   cylinder()       synthetic 8-patch non-matching cylinder (BASELINE C3)
   wingbox()        synthetic 40-patch wing box with T- and X-junction intersections (BASELINE C4)
+  twisted_beam()   MacNeal-Harder twisted beam on two non-matching patches (known answer, tests only)
 
 Layout conventions: scalar CP index a = i + j*n_u; patch-local vector dof
 = field*n_cp + a; global dofs = patches concatenated in list order
@@ -281,6 +282,48 @@ def wingbox(h=0.05, n_seg=10, n_spar=3, n_rib=17, L=10.0, C=2.0, H=0.4, p=3, E=6
             itf(a, [[x / L, 0.], [x / L, 1.]], b, [[ur, 0.], [ur, 1.]], meta[a][1], meta[b][1])
     return dict(name=f"wingbox_{len(patches)}p_h{h:.4g}", patches=patches, E=E, nu=nu, interfaces=interfaces,
                 penalty_coefficient=penalty_coefficient, point_loads=[], edge_loads=[])
+
+
+def _twisted_strip(s0, s1, L, w, ne_u, ne_v, p=3):
+    """Bicubic patch of the 90-degree twisted strip X = (r cos phi, r sin phi, s), phi = pi s / (2 L), s in [s0, s1]:
+    exact in r (linear, degree elevated), cubic B-spline interpolation at the Greville points in s."""
+    kv = np.concatenate([np.zeros(p), np.linspace(0, 1, ne_v + 1), np.ones(p)])
+    n = len(kv) - p - 1
+    g = np.array([kv[j + 1:j + p + 1].mean() for j in range(n)])
+    span, B = bsp.basis_window(kv, p, g, 0)
+    Cm = np.zeros((n, n))
+    for i in range(n):
+        Cm[i, span[i] - p:span[i] + 1] = B[i, 0]
+    s = s0 + (s1 - s0) * g
+    phi = 0.5 * np.pi * s / L
+    coef = np.linalg.solve(Cm, np.stack([np.cos(phi), np.sin(phi), s], 1))
+    ctrl = np.zeros((2, n, 4))
+    for i, r in enumerate((-0.5 * w, 0.5 * w)):
+        ctrl[i, :, 0] = r * coef[:, 0]; ctrl[i, :, 1] = r * coef[:, 1]; ctrl[i, :, 2] = coef[:, 2]; ctrl[i, :, 3] = 1.0
+    srf = bsp.NURBSSurface([[0., 0., 1., 1.], kv], [1, p], ctrl)
+    srf.elevate(0, p - 1)
+    srf.refine(0, np.linspace(0, 1, ne_u + 1)[1:-1])
+    return srf
+
+
+def twisted_beam(ne=16, tip_force=(0.0, 1.0, 0.0), L=12.0, w=1.1, t=0.32, E=29.0e6, nu=0.22, penalty_coefficient=1.0e3):
+    """MacNeal-Harder twisted beam (90-degree twist, root clamped, unit tip force) as TWO non-matching bicubic patches
+    coupled by the penalty method: a known answer on doubly curved geometry with nu != 0.  Reference tip displacements
+    in the load direction: 5.424e-3 for the in-plane load (tip width direction, global y) and 1.754e-3 for the
+    out-of-plane load (global x); a Kirchhoff-Love shell (no transverse shear) gives 0.995 of both."""
+    th = dict(kind="const", values=t)
+    cuts = [0.0, 0.45 * L, L]
+    nes = [(3, ne), (4, ne + 3)]
+    patches = []
+    for k in range(2):
+        srf = _twisted_strip(cuts[k], cuts[k + 1], L, w, nes[k][0], nes[k][1])
+        bc = [(f, 1, 0, 2) for f in range(3)] if k == 0 else []
+        patches.append(_patch_from_surface(srf, 9, th, bc, (0.0, 0.0, 0.0)))
+    n_m = 2 * max(nes[0][0], nes[1][0]) + 4
+    itf = [dict(patches=(0, 1), xi=(mortar_coords([[0., 1.], [1., 1.]], n_m), mortar_coords([[0., 0.], [1., 0.]], n_m)))]
+    loads = [dict(patch=1, field=f, xi=(0.5, 1.0), value=-tip_force[f]) for f in range(3) if tip_force[f] != 0.0]
+    return dict(name="twisted_beam", patches=patches, E=E, nu=nu, interfaces=itf, penalty_coefficient=penalty_coefficient,
+                point_loads=loads, edge_loads=[])
 
 
 def num_dofs(problem):

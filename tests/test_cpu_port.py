@@ -156,3 +156,23 @@ def test_pinched_free_cylinder_known_answer():
     s = np.sqrt(0.5)
     w = 0.5 * _radial_approach(cm, u, [(0, (0.5, 1.0), (s, s)), (2, (0.5, 1.0), (-s, -s))])
     assert abs(w / 0.1139 - 1.0) < 1.5e-2
+
+
+def test_twisted_beam_known_answer():
+    """MacNeal-Harder twisted beam (L = 12, w = 1.1, t = 0.32, E = 29e6, nu = 0.22, 90-degree twist, unit tip loads) on two
+    NON-MATCHING patches: tip displacement in the load direction 5.424e-3 (in-plane) / 1.754e-3 (out-of-plane); a
+    Kirchhoff-Love shell has no transverse shear and converges to 0.995 of both.  Doubly curved geometry, nu != 0, penalty
+    coupling; Maxwell-Betti reciprocity of the two load cases is checked too."""
+    from goldfish_b200 import problems, bsplines as bsp
+    tips = {}
+    for name, F in (("in", (0.0, 1.0, 0.0)), ("out", (1.0, 0.0, 0.0))):
+        pr = problems.twisted_beam(16, F)
+        cm = CpuModel(pr)
+        cm.set_u(np.zeros(cm.S.N)); cm.assemble(capi.GF_OUT_R | capi.GF_OUT_K)
+        u = cm.solve(-cm.residual())
+        P = cm.S.patches[1]
+        conn, D = bsp.surface_point_tables(P.ku, P.kv, 3, 3, np.ones(P.ncp), np.array([[0.5, 1.0]]))
+        tips[name] = np.array([(D[0, 0] * u[P.dof_off + f * P.ncp + conn[0]]).sum() for f in range(3)])
+    assert 0.990 < tips["in"][1] / 5.424e-3 < 1.0
+    assert 0.990 < tips["out"][0] / 1.754e-3 < 1.0
+    assert abs(tips["in"][0] - tips["out"][1]) < 1e-6 * abs(tips["in"][0])       # u_x(F_y) = u_y(F_x)
