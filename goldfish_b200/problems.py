@@ -12,6 +12,7 @@ intersections with their mortar parametric coordinates.
   cylinder()       synthetic 8-patch non-matching cylinder (BASELINE C3)
   wingbox()        synthetic 40-patch wing box with T- and X-junction intersections (BASELINE C4)
   twisted_beam()   MacNeal-Harder twisted beam on two non-matching patches (known answer, tests only)
+  hemisphere()     pinched hemisphere with an 18-degree hole on four non-matching NURBS patches (known answer, tests only)
 
 Layout conventions: scalar CP index a = i + j*n_u; patch-local vector dof
 = field*n_cp + a; global dofs = patches concatenated in list order
@@ -323,6 +324,70 @@ def twisted_beam(ne=16, tip_force=(0.0, 1.0, 0.0), L=12.0, w=1.1, t=0.32, E=29.0
     itf = [dict(patches=(0, 1), xi=(mortar_coords([[0., 1.], [1., 1.]], n_m), mortar_coords([[0., 0.], [1., 0.]], n_m)))]
     loads = [dict(patch=1, field=f, xi=(0.5, 1.0), value=-tip_force[f]) for f in range(3) if tip_force[f] != 0.0]
     return dict(name="twisted_beam", patches=patches, E=E, nu=nu, interfaces=itf, penalty_coefficient=penalty_coefficient,
+                point_loads=loads, edge_loads=[])
+
+
+def _arc3(P0, P2, center):
+    """Rational quadratic arc from P0 to P2 on the circle around `center` (sweep < 180 deg): homogeneous control points."""
+    P0, P2, center = (np.asarray(v, dtype=np.float64) for v in (P0, P2, center))
+    a, b = P0 - center, P2 - center
+    R = np.linalg.norm(a)
+    w = np.cos(0.5 * np.arccos(np.clip(a @ b / (R * R), -1.0, 1.0)))
+    m = a + b
+    m = m / np.linalg.norm(m) * (R / w)
+    c = np.zeros((3, 4))
+    for r, (P, wt) in enumerate(((a, 1.0), (m, w), (b, 1.0))):
+        c[r, :3] = (center + P) * wt; c[r, 3] = wt
+    return c
+
+
+def _sphere_patch(R, th0, th1, ph0, ph1, ne_u, ne_v, p=3):
+    """Exact NURBS patch of a sphere: u = azimuth in [ph0, ph1], v = polar angle in [th0, th1] (biquadratic rational
+    surface of revolution, elevated to degree p, refined)."""
+    mer = _arc3([R * np.sin(th0), 0, R * np.cos(th0)], [R * np.sin(th1), 0, R * np.cos(th1)], [0, 0, 0])
+    ctrl = np.zeros((3, 3, 4))
+    for j in range(3):
+        wj = mer[j, 3]; xj = mer[j, 0] / wj; zj = mer[j, 2] / wj
+        az = _arc3([xj * np.cos(ph0), xj * np.sin(ph0), zj], [xj * np.cos(ph1), xj * np.sin(ph1), zj], [0, 0, zj])
+        for i in range(3):
+            wi = az[i, 3]
+            ctrl[i, j, :3] = az[i, :3] / wi * (wi * wj); ctrl[i, j, 3] = wi * wj
+    k = [0., 0., 0., 1., 1., 1.]
+    srf = bsp.NURBSSurface([k, k], [2, 2], ctrl)
+    srf.elevate(0, p - 2); srf.elevate(1, p - 2)
+    srf.refine(0, np.linspace(0, 1, ne_u + 1)[1:-1]); srf.refine(1, np.linspace(0, 1, ne_v + 1)[1:-1])
+    return srf
+
+
+def hemisphere(ne=16, R=10.0, t=0.04, E=6.825e7, nu=0.3, F=2.0, hole_deg=18.0, penalty_coefficient=1.0e3):
+    """Pinched hemisphere with an 18-degree hole (shell obstacle course, MacNeal-Harder): four NON-MATCHING exact NURBS
+    patches (90 degrees of azimuth each, ne + k elements per side) closed into a ring by penalty coupling, alternating
+    radial forces +-F on the equator at 0, 90, 180, 270 degrees (patch corners), six statically determinate supports.
+    Reference radial displacement under the loads: 0.0940.  Inextensional bending of a doubly curved rational surface."""
+    th = dict(kind="const", values=t)
+    patches, nes = [], []
+    for k in range(4):
+        nes.append(ne + k)
+        srf = _sphere_patch(R, np.radians(hole_deg), np.radians(90.0), k * np.pi / 2, (k + 1) * np.pi / 2, ne + k, ne + k)
+        patches.append(_patch_from_surface(srf, 9, th, [], (0.0, 0.0, 0.0)))
+    itf = []
+    for k in range(4):
+        a, b = k, (k + 1) % 4
+        n_m = 2 * max(nes[a], nes[b])
+        itf.append(dict(patches=(a, b), xi=(mortar_coords([[1., 0.], [1., 1.]], n_m), mortar_coords([[0., 0.], [0., 1.]], n_m))))
+    loads = []
+    for k in range(4):                                   # corner (u = 0, v = 1) of patch k = equator at azimuth k * 90 deg
+        er = np.array([np.cos(k * np.pi / 2), np.sin(k * np.pi / 2)])
+        sgn = 1.0 if k % 2 == 0 else -1.0
+        loads += [dict(patch=k, field=f, xi=(0.0, 1.0), value=-sgn * F * er[f]) for f in range(2) if abs(er[f]) > 1e-12]
+    P0, P2 = patches[0], patches[2]
+    n_u, n_v = len(P0["knots"][0]) - 4, len(P0["knots"][1]) - 4
+    ncp, a0, a1 = n_u * n_v, (n_v - 1) * n_u, (n_v - 1) * n_u + n_u - 1
+    P0["bc_dofs"] = np.array([2 * ncp + a0, 2 * ncp + a1, ncp + a0, a1], dtype=np.int64)      # u_z at 0 and 90 deg, tangential there
+    n_u2, n_v2 = len(P2["knots"][0]) - 4, len(P2["knots"][1]) - 4
+    ncp2, b0 = n_u2 * n_v2, (n_v2 - 1) * n_u2
+    P2["bc_dofs"] = np.array([2 * ncp2 + b0, ncp2 + b0], dtype=np.int64)                      # u_z and tangential u_y at 180 deg
+    return dict(name="hemisphere", patches=patches, E=E, nu=nu, interfaces=itf, penalty_coefficient=penalty_coefficient,
                 point_loads=loads, edge_loads=[])
 
 

@@ -176,3 +176,25 @@ def test_twisted_beam_known_answer():
     assert 0.990 < tips["in"][1] / 5.424e-3 < 1.0
     assert 0.990 < tips["out"][0] / 1.754e-3 < 1.0
     assert abs(tips["in"][0] - tips["out"][1]) < 1e-6 * abs(tips["in"][0])       # u_x(F_y) = u_y(F_x)
+
+
+def test_pinched_hemisphere_known_answer():
+    """Pinched hemisphere with an 18-degree hole (R = 10, t = 0.04, E = 6.825e7, nu = 0.3, F = +-2): radial displacement
+    under the loads 0.0940 (shell obstacle course).  Four NON-MATCHING exact NURBS patches closed into a ring: nearly
+    inextensional bending of a doubly curved RATIONAL surface -- the case that exposes membrane locking and any error in
+    the rational basis derivatives or the curvature terms."""
+    from goldfish_b200 import problems, bsplines as bsp
+    pr = problems.hemisphere(16)
+    cm = CpuModel(pr)
+    cm.set_u(np.zeros(cm.S.N)); cm.assemble(capi.GF_OUT_R | capi.GF_OUT_K)
+    u = cm.solve(-cm.residual())
+    rad = []
+    for k in range(4):
+        P = cm.S.patches[k]
+        conn, D = bsp.surface_point_tables(P.ku, P.kv, 3, 3, P.cp[:, 3], np.array([[0.0, 1.0]]))
+        d = np.array([(D[0, 0] * u[P.dof_off + f * P.ncp + conn[0]]).sum() for f in range(3)])
+        rad.append(d[0] * np.cos(k * np.pi / 2) + d[1] * np.sin(k * np.pi / 2))
+    rad = np.array(rad)
+    assert np.all(rad[[0, 2]] > 0) and np.all(rad[[1, 3]] < 0)                 # outward under +F, inward under -F
+    assert 0.985 < np.mean(np.abs(rad)) / 0.0940 < 1.0
+    assert np.ptp(np.abs(rad)) < 2e-3 * np.mean(np.abs(rad))                   # the four non-matching patches agree
