@@ -12,6 +12,7 @@ intersections with their mortar parametric coordinates.
   cylinder()       synthetic 8-patch non-matching cylinder (BASELINE C3)
   wingbox()        synthetic 40-patch wing box with T- and X-junction intersections (BASELINE C4)
   twisted_beam()   MacNeal-Harder twisted beam on two non-matching patches (known answer, tests only)
+  cantilever_shear()  geometrically nonlinear cantilever under end shear (Sze et al. 2004; known answer, tests only)
   hemisphere()     pinched hemisphere with an 18-degree hole on four non-matching NURBS patches (known answer, tests only)
 
 Layout conventions: scalar CP index a = i + j*n_u; patch-local vector dof
@@ -389,6 +390,26 @@ def hemisphere(ne=16, R=10.0, t=0.04, E=6.825e7, nu=0.3, F=2.0, hole_deg=18.0, p
     P2["bc_dofs"] = np.array([2 * ncp2 + b0, ncp2 + b0], dtype=np.int64)                      # u_z and tangential u_y at 180 deg
     return dict(name="hemisphere", patches=patches, E=E, nu=nu, interfaces=itf, penalty_coefficient=penalty_coefficient,
                 point_loads=loads, edge_loads=[])
+
+
+def cantilever_shear(P=4.0, ne=8, L=10.0, b=1.0, t=0.1, E=1.2e6, nu=0.0, penalty_coefficient=1.0e3):
+    """Cantilever strip under an end shear force (Sze, Liu & Lo 2004, the standard geometrically NONLINEAR shell
+    benchmark: L = 10, b = 1, t = 0.1, E = 1.2e6, nu = 0, P_max = 4) as two non-matching patches along the length;
+    total force P as a dead traction on the tip edge.  Tip deflections (-u_x, u_z): P = 1: (0.563, 3.015),
+    P = 2: (1.603, 4.933), P = 4: (3.286, 6.698)."""
+    th = dict(kind="const", values=t)
+    cuts = [0.0, 0.4 * L, L]
+    nes = [(2, ne), (3, ne + 3)]
+    patches = []
+    for k in range(2):
+        pts = [[cuts[k], 0, 0], [cuts[k], b, 0], [cuts[k + 1], 0, 0], [cuts[k + 1], b, 0]]     # u: width (y), v: length (x)
+        srf = _ruled_quad(pts, nes[k][0], nes[k][1], 3)
+        bc = [(f, 1, 0, 2) for f in range(3)] if k == 0 else []
+        patches.append(_patch_from_surface(srf, 9, th, bc, (0.0, 0.0, 0.0)))
+    itf = [dict(patches=(0, 1), xi=(mortar_coords([[0., 1.], [1., 1.]], 10), mortar_coords([[0., 0.], [1., 0.]], 10)))]
+    edge = [dict(patch=1, direction=1, side=1, traction=(0.0, 0.0, P / b))]
+    return dict(name="cantilever_shear", patches=patches, E=E, nu=nu, interfaces=itf, penalty_coefficient=penalty_coefficient,
+                point_loads=[], edge_loads=edge)
 
 
 def num_dofs(problem):
