@@ -138,3 +138,18 @@ def test_oracle_regression_goldens():
     K = m.stiffness()
     assert np.array_equal(K.indptr, g["K_indptr"]) and np.array_equal(K.indices, g["K_indices"])
     assert np.abs(K.data - g["K_data"]).max() <= 1e-12 * np.abs(g["K_data"]).max()
+
+
+def test_oracle_nonlinear_cantilever_known_answer():
+    """The INDEPENDENT numpy oracle (second-order jets of one energy expression) on the geometrically nonlinear cantilever
+    of Sze, Liu & Lo (2004), P = 1 of P_max = 4: tip deflections (0.563, 3.015).  Pins the oracle's own tangent and
+    large-rotation kinematics against published values, not only against the compiled port."""
+    from goldfish_b200 import problems
+    from oracle import bspline as obs
+    om = OracleModel(problems.cantilever_shear(1.0, ne=4))
+    u = om.solve_nonlinear(max_it=30, rtol=1e-7)
+    assert om.newton_history[-1] < 1e-7 and len(om.newton_history) < 20
+    P = om.patches[1]
+    conn, D = obs.surface_basis(P.ku, P.kv, 3, 3, P.cp[:, 3], np.array([[0.5, 1.0]]))
+    d = np.array([(D[0, 0] * u[P.off + f * P.ncp + conn[0]]).sum() for f in range(3)])
+    assert abs(-d[0] / 0.563 - 1.0) < 6e-3 and abs(d[2] / 3.015 - 1.0) < 3e-3
