@@ -62,17 +62,33 @@ class OracleBackend:
         self.cpdes_iga_nest = [NpVec(np.zeros(n_sc), self) for _ in self.opt_field]
         self.h_th_nest = NpVec(np.zeros(self.om.n_th), self)
         self.dm = self
+        self._cache = {}
+
+    def _cached(self, key, fn):
+        """The oracle is slow and this test is about the facade, not the operators: evaluate each operator once per state."""
+        k = (key, self.om.u.tobytes())
+        if k not in self._cache:
+            self._cache[k] = fn()
+        return self._cache[k]
 
     def solve(self, b, x):                       # what opt_utils._solve calls on the matrix owner
-        x[:] = spla.splu(self.om.stiffness().tocsc()).solve(b)
+        lu = self._cached("lu", lambda: spla.splu(self.om.stiffness().tocsc()))
+        x[:] = lu.solve(b)
 
-    def RIGA(self): return NpVec(self.om.residual(), self)
-    def dRIGAduIGA(self): return NpMat(self.om.stiffness(), self, is_K=True)
-    def dRIGAdCPIGA(self, field): return NpMat(self.om.dRdCP(field, self.surf[self.opt_field.index(field)]), self)
-    def dRIGAdh_th(self): return NpMat(self.om.dRdt(), self)
+    def RIGA(self): return NpVec(self._cached("R", self.om.residual), self)
+    def dRIGAduIGA(self): return NpMat(self._cached("K", self.om.stiffness), self, is_K=True)
+
+    def dRIGAdCPIGA(self, field):
+        return NpMat(self._cached(("P", field), lambda: self.om.dRdCP(field, self.surf[self.opt_field.index(field)])), self)
+
+    def dRIGAdh_th(self): return NpMat(self._cached("T", self.om.dRdt), self)
 
     def solve_nonlinear_nonmatching_problem(self, max_it=30, zero_mortar_funcs=True, rtol=1e-3, iga_dofs=True):
-        return None, NpVec(self.om.solve_nonlinear(max_it=max_it, rtol=rtol), self)
+        k = ("newton", max_it, rtol)
+        if k not in self._cache:
+            self._cache[k] = self.om.solve_nonlinear(max_it=max_it, rtol=rtol)
+        self.om.set_u(self._cache[k])
+        return None, NpVec(self._cache[k], self)
 
 
 def _load_reference_class():
