@@ -42,7 +42,7 @@ def coarsening_ratio(problem, target_dofs, r_min=7.0):
 def build(problem, nc=8, ratio=None):
     """Returns (coarse_problem, P) with P the (N x Nc) scipy CSR prolongation.  nc: coarse elements per side of
     every patch; ratio (overrides nc): fine elements per coarse element, per direction and patch."""
-    patches_c, blocks = [], []
+    patches_c, blocks, restrict = [], [], []
     for pd in problem["patches"]:
         p = pd["p"][0]
         ku, kv = [np.asarray(k, dtype=np.float64) for k in pd["knots"]]
@@ -61,6 +61,7 @@ def build(problem, nc=8, ratio=None):
         Xc = np.linalg.lstsq(Pu, Xc.transpose(1, 0, 2).reshape(n_u, -1), rcond=None)[0]
         Xc = Xc.reshape(Pu.shape[1], Pv.shape[1], 4).transpose(1, 0, 2)
         nc_u, nc_v = Pu.shape[1], Pv.shape[1]
+        restrict.append((np.linalg.pinv(Pv), np.linalg.pinv(Pu)))             # least-squares restriction of a control net
         P2 = sp.kron(sp.csr_matrix(Pv), sp.csr_matrix(Pu), format="csr")      # (n_v n_u) x (nc_v nc_u)
         ncp, ncpc = n_u * n_v, nc_u * nc_v
         # coarse zero-dofs: a coarse dof is constrained iff its dominant fine dof is
@@ -75,7 +76,28 @@ def build(problem, nc=8, ratio=None):
         blocks.append(sp.block_diag([P2, P2, P2], format="csr"))
     coarse = dict(name=problem.get("name", "") + "_coarse", patches=patches_c, E=problem["E"], nu=problem["nu"],
                   interfaces=problem.get("interfaces", []), penalty_coefficient=problem.get("penalty_coefficient", 1e3),
-                  point_loads=[], edge_loads=[])
+                  point_loads=[], edge_loads=[], restrict=restrict)
     P = sp.block_diag(blocks, format="csr")
     P.sort_indices()
     return coarse, P
+
+
+def restrict_design(coarse, cp_fine, theta_fine, fine_patches):
+    """Coarse control net and thickness of the CURRENT design: per patch the least-squares inverse of the knot
+    insertion applied to the fine homogeneous control net (the same map `build` applies to the initial design), and
+    the patch mean of the thickness dofs.  cp_fine: [n_scalar, 4]; fine_patches: (n_u, n_v, cp_off, th_off, nth) per
+    patch.  Returns (cp_coarse [n_scalar_c, 4], theta_coarse [n_patches])."""
+    cps, ths = [], []
+    for (Rv, Ru), (n_u, n_v, cp_off, th_off, nth) in zip(coarse["restrict"], fine_patches):
+        X = np.asarray(cp_fine[cp_off:cp_off + n_u * n_v], dtype=np.float64).reshape(n_v, n_u, 4)
+        Xc = np.einsum("av,vuk->auk", Rv, X)
+        Xc = np.einsum("bu,auk->abk", Ru, Xc)                                  # [nc_v, nc_u, 4]
+        cps.append(Xc.reshape(-1, 4))
+        ths.append(float(np.mean(theta_fine[th_off:th_off + nth])))
+    return np.concatenate(cps), np.asarray(ths)
+
+
+def refresh_due(its, its_ref, design_changed, growth=1.6, slack=10):
+    """Iteration-growth trigger of the automatic coarse refresh: the coarse level belongs to an older design and the
+    first Krylov pass needs clearly more iterations than it did right after the level was built."""
+    return bool(design_changed and its_ref is not None and its > growth * its_ref + slack)

@@ -279,6 +279,13 @@ class DeviceModel:
         self.stats = {"launches": 0}
         self.state_epoch = 0
         self._epochs = {}
+        # coarse-level refresh policy (opt-in automation: the iteration-growth trigger has not been measured on an
+        # optimisation run yet; refresh_coarse() itself is what an optimiser driver calls every few design updates)
+        self.design_epoch = 0
+        self._coarse_design_epoch = 0
+        self.auto_refresh_coarse = False
+        self._its_ref = None
+        self._want_coarse_refresh = False
         if lean:
             # >= 10 M dof runs: the index arrays of K / dR/dCP / dR/dt and the coupling lists live in HBM from here on;
             # drop the host copies (GBs per rank) once the transpose structures that are built from them exist
@@ -411,6 +418,7 @@ class DeviceModel:
         if torch.equal(th, self.theta):
             return
         self.theta.copy_(th)
+        self.design_epoch += 1
         self.touch()
 
     def set_cp(self, field, arr, surf_inds=None):
@@ -425,6 +433,7 @@ class DeviceModel:
             cpv[P.cp_off:P.cp_off + P.ncp, field].copy_(arr[o:o + P.ncp], non_blocking=True)
             o += P.ncp
         assert o == arr.numel()
+        self.design_epoch += 1
         self.touch()
 
     def get_cp(self, field, surf_inds=None):
@@ -559,6 +568,7 @@ class DeviceModel:
                 from . import coarse as coarse_mod
                 cpr, P = coarse_mod.build(self.problem, nc=self.coarse_nc, ratio=self.coarse_ratio)
                 cpr["alpha_override"] = self.sym.itf_alpha
+                self._coarse_problem = cpr
                 cm = DeviceModel(cpr, device=self.device, precond="schwarz", coarse_nc=0, distributed=False)
                 cm._single_block = True
                 Pd = DeviceCsr(P.shape[0], P.shape[1], P.indptr, P.indices, self.device)
@@ -674,12 +684,30 @@ class DeviceModel:
         pc.cinv, pc.cinv_row0, pc.cinv_rows = _ptr(self._cinv), r0, r1 - r0
 
     def refresh_coarse(self):
-        """Re-assemble and re-factor the coarse level at the next preconditioner set-up."""
+        """Bring the coarse level to the CURRENT design and re-factor it at the next preconditioner set-up: the coarse
+        control net is the least-squares restriction of the current fine control net (the map that built it from the
+        initial design), the coarse thickness the patch means of the current thickness dofs."""
         self._coarse_factored = False
+        self._its_ref = None
+        self._want_coarse_refresh = False
+        if getattr(self, "_coarse", None) is None:
+            return
+        from . import coarse as coarse_mod
+        cm = self._coarse[0]
+        S = self.sym
+        cpc, thc = coarse_mod.restrict_design(self._coarse_problem, self.cp.detach().cpu().numpy().reshape(-1, 4),
+                                              self.theta.detach().cpu().numpy(),
+                                              [(P.n_u, P.n_v, P.cp_off, P.th_off, P.nth) for P in S.patches])
+        cm.cp.copy_(torch.from_numpy(np.ascontiguousarray(cpc)).to(self.device).reshape(cm.cp.shape))
+        cm.theta.copy_(torch.from_numpy(thc).to(self.device))
+        cm.touch()
+        self._coarse_design_epoch = self.design_epoch
 
     def factor_preconditioner(self, _reference=False):
         """(Re)build the preconditioner from the current K values."""
         st = self._stream()
+        if self._want_coarse_refresh:
+            self.refresh_coarse()
         self.replicate_K()
         cs = self.K.c_struct()
         if self.precond == "schwarz":
@@ -754,6 +782,12 @@ class DeviceModel:
         bn = self.dot(b, b) ** 0.5
         its, rel = self._krylov(b, x, self.pass_rtol, max_it)
         self.last_krylov_its, self.last_relres = its, rel
+        if self.auto_refresh_coarse and getattr(self, "_coarse", None) is not None:
+            from .coarse import refresh_due
+            if self._its_ref is None:
+                self._its_ref = its                   # first solve after the coarse level was (re)built
+            elif refresh_due(its, self._its_ref, self.design_epoch != self._coarse_design_epoch):
+                self._want_coarse_refresh = True      # acted upon at the next factorisation
         if not bn > 0.0:                  # zero right-hand side: x = 0 exactly
             self.last_true_relres = 0.0
             return x

@@ -93,3 +93,28 @@ def test_subdomain_and_coarse_rules():
     spar = cwb["patches"][20]
     neu, nev = len(np.unique(spar["knots"][0])) - 1, len(np.unique(spar["knots"][1])) - 1
     assert neu > 3 * nev and nev >= 8 and Pw.shape[1] <= 24000
+
+
+def test_coarse_design_restriction_and_refresh_trigger():
+    """refresh_coarse(): the coarse control net of the CURRENT design is the least-squares restriction of the fine net --
+    the initial design gives back the coarse net `build` made, a design that lies in the coarse space is reproduced
+    exactly, thickness becomes the patch mean; the automatic trigger fires only for a changed design and a clear growth."""
+    pr = problems.cylinder(n_el=24)
+    S = Symbolic(pr)
+    cpr, P = coarse.build(pr, ratio=7.0)
+    fine = [(Pp.n_u, Pp.n_v, Pp.cp_off, Pp.th_off, Pp.nth) for Pp in S.patches]
+    cpc, thc = coarse.restrict_design(cpr, S.cp0, S.theta0, fine)
+    assert np.abs(cpc - np.concatenate([p["cp"] for p in cpr["patches"]])).max() < 1e-10
+    assert np.allclose(thc, [p["thickness"]["values"] for p in cpr["patches"]])
+    # a perturbation taken from the coarse space is recovered exactly: restrict(prolong(dXc)) = dXc
+    Sc = Symbolic(cpr)
+    rng = np.random.default_rng(0)
+    dXc = rng.standard_normal((Sc.n_scalar, 4)) * 1e-3
+    dX = np.zeros_like(S.cp0)
+    for Pf, Pc in zip(S.patches, Sc.patches):
+        blk = P[Pf.dof_off:Pf.dof_off + Pf.ncp, Pc.dof_off:Pc.dof_off + Pc.ncp]
+        dX[Pf.cp_off:Pf.cp_off + Pf.ncp] = blk @ dXc[Pc.cp_off:Pc.cp_off + Pc.ncp]
+    cpc2, _ = coarse.restrict_design(cpr, S.cp0 + dX, 1.1 * S.theta0, fine)
+    assert np.abs(cpc2 - (cpc + dXc)).max() < 1e-10
+    assert coarse.refresh_due(120, 60, True) and not coarse.refresh_due(120, 60, False)
+    assert not coarse.refresh_due(100, 60, True) and not coarse.refresh_due(500, None, True)

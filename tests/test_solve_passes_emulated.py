@@ -36,6 +36,7 @@ class Stub:
         self.true_rtol, self.pass_rtol, self.max_refine, self.polish, self.krylov_rtol = 1e-8, 1e-6, 3, polish, 1e-11
         self._sw_factored, self.eager_refactor, self._fact_version, self._K_version = True, False, 0, 0
         self._w_res = self._w_cor = None
+        self.auto_refresh_coarse = False
         self.lib = _Lib(self)
         self.calls = []
         self.K = type("K", (), {"c_struct": lambda s: C.c_int(0)})()
